@@ -1,0 +1,184 @@
+/* reentry_b200.h -- C ABI of the B200-native ensemble trajectory propagator.
+ *
+ * Drop-in boundary for the ONE hot path of JMMonte/Reentry-OLD: the trajectory
+ * integration behind SpacecraftModel.run_simulation (spacecraft_model.py:490-519) and the
+ * acceleration evaluation it drives (spacecraft_model.py:437-470), run for ensembles of
+ * independent initial states.  The reference has no FFI of its own (it is pure Python +
+ * numba); each entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only: no torch / numpy / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = RB_OK, negative = rb_error (rb_strerror()).
+ *   - device pointers are plain CUDA device addresses on the context's device; the CALLER
+ *     allocates and frees every buffer it passes; the library owns only its context
+ *     (time table, live-index workspace, counters).
+ *   - work is enqueued on the cudaStream_t passed as `void* stream` (NULL = legacy default
+ *     stream).  Nothing synchronises unless stated (rb_ctx_destroy, RB_FLAG_EARLY_EXIT
+ *     polling, the *_host convenience calls).
+ *   - a context is bound to one device, is not re-entrant, one per rank/GPU.
+ *   - per-trajectory numerical failures are reported in status[i], never as a process abort.
+ *   - all floating point is IEEE float64; time is seconds from the model epoch.
+ *
+ * Fixed-step contract: Dormand-Prince 5(4) with scipy's RK45 tableau
+ * (scipy/integrate/_ivp/rk.py:541-565), FSAL, t_{n+1} = t_n + dt, stage times t_n + C_s*dt;
+ * event g = |r| - 6378137 - event_altitude, active in the step where g_old >= 0 and
+ * g_new <= 0 (scipy ivp.py:151, direction -1); impact time = root of g on the step's
+ * quartic dense output (rk.py:554-565, 723-737).
+ */
+#ifndef REENTRY_B200_H
+#define REENTRY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+#define RB_TABLE_ENTRY_DOUBLES 16 /* one time-table entry = 128 B */
+#define RB_STAGES_PER_STEP 5      /* distinct new stage times per DP5 step (c = 1/5, 3/10, 4/5, 8/9, 1) */
+#define RB_SAMPLE_FIELDS 8        /* x, y, z, vx, vy, vz, altitude, speed */
+
+typedef enum rb_error {
+    RB_OK = 0,
+    RB_ERR_INVALID_ARG = -1,
+    RB_ERR_CUDA = -2,       /* rb_ctx_last_error() has the CUDA text */
+    RB_ERR_NO_TIME_TABLE = -3,
+    RB_ERR_TABLE_RANGE = -4, /* run asks for steps the staged time table does not cover */
+    RB_ERR_NOMEM = -5,
+    RB_ERR_NO_DEVICE = -6
+} rb_error;
+
+/* status[i] values */
+typedef enum rb_traj_status {
+    RB_TRAJ_ALIVE = 0,     /* reached n_steps without an event */
+    RB_TRAJ_IMPACTED = 1,  /* terminal altitude event fired (spacecraft_model.py:496-504) */
+    RB_TRAJ_NONFINITE = 2  /* state became NaN/Inf; lane retired */
+} rb_traj_status;
+
+/* run flags */
+#define RB_FLAG_COMPACT 1u      /* order-preserving compaction of live trajectories between launches */
+#define RB_FLAG_EARLY_EXIT 2u   /* host polls the live count (2 launches behind) and stops when it is 0 */
+#define RB_FLAG_NO_REFINE 4u    /* skip the dense-output impact-time refinement (impact_time = NaN) */
+#define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
+                                   synchronises the stream at the end and rb_stats.propagate_ms is valid */
+
+typedef struct rb_ctx rb_ctx;
+
+int32_t rb_abi_version(void);
+const char *rb_strerror(int32_t code);
+const char *rb_ctx_last_error(const rb_ctx *ctx);
+
+/* Replaces SpacecraftModel.__init__ (spacecraft_model.py:393-410) for the path: binds a
+ * device; the physical constants are compiled in from include/reentry_constants.h. */
+int32_t rb_ctx_create(rb_ctx **out, int32_t device);
+int32_t rb_ctx_destroy(rb_ctx *ctx); /* synchronises the device */
+
+/* ---- time table: everything in the RHS that depends on time only -------------------
+ * Entry e (16 doubles): sun[3], moon[3] (sun/moon_position_vector, spacecraft_model.py:
+ * 270-344), k*s/|s|^3 for Sun and Moon (indirect term of third_body_acceleration, :362),
+ * cos/sin(gmst0 + EARTH_OMEGA*t) (:443, coordinate_converter.py:32-33), the time part of
+ * solar_activity_factor (:151-159), t.  Entry 0 is t0; step n owns entries 1+5n .. 5+5n
+ * (stage times t_n + C_s*dt, s = 1..5; the FSAL evaluation at t_n + dt reuses entry 5+5n). */
+int64_t rb_time_table_entries(int64_t n_steps); /* 5*n_steps + 1 */
+
+/* Host builder (libm, optional OpenMP threads; n_threads <= 0 = all).  host_table must
+ * hold rb_time_table_entries(n_steps) * 16 doubles. */
+int32_t rb_build_time_table(double epoch_jd, double gmst0, double t0, double dt, int64_t n_steps,
+                            double *host_table, int32_t n_threads);
+
+/* Upload a host table (copied; the context owns the device copy). */
+int32_t rb_ctx_set_time_table(rb_ctx *ctx, const double *host_table, int64_t n_steps, double t0,
+                              double dt, void *stream);
+
+/* ---- initial states: batched SpacecraftModel.get_initial_state (spacecraft_model.py:412-435)
+ * Inputs are device arrays [n] (v m/s, lat deg, lon deg, alt m, azimuth deg, gamma deg);
+ * y0 is written SoA: y0[c * y0_comp_stride + i * y0_traj_stride]. */
+int32_t rb_initial_states(rb_ctx *ctx, int64_t n, const double *v, const double *lat, const double *lon,
+                          const double *alt, const double *azimuth, const double *gamma, double gmst,
+                          double *y0, int64_t y0_traj_stride, int64_t y0_comp_stride, void *stream);
+
+/* ---- propagation ------------------------------------------------------------------- */
+typedef struct rb_in {
+    int64_t n;               /* trajectories */
+    const double *y0;        /* device; element (i, c) at y0[i*y0_traj_stride + c*y0_comp_stride] */
+    int64_t y0_traj_stride;  /* AoS [n][6]: 6, SoA [6][n]: 1 */
+    int64_t y0_comp_stride;  /* AoS: 1, SoA: n */
+    const double *cd;        /* device [n] or NULL -> cd_scalar  (SpacecraftModel.Cd) */
+    const double *area;      /* device [n] or NULL -> area_scalar (SpacecraftModel.A) */
+    const double *mass;      /* device [n] or NULL -> mass_scalar (SpacecraftModel.m) */
+    double cd_scalar, area_scalar, mass_scalar;
+} rb_in;
+
+typedef struct rb_run {
+    int64_t first_step;       /* index of the first step within the staged time table (normally 0) */
+    int64_t n_steps;          /* steps to take (cap for "until impact") */
+    int64_t out_stride;       /* store every out_stride-th step (>= 1); sample k = step k*out_stride */
+    int64_t steps_per_launch; /* compaction period in steps; 0 = library default (32) */
+    double event_altitude;    /* 1000.0 in the reference (spacecraft_model.py:501) */
+    uint32_t flags;           /* RB_FLAG_* */
+    uint32_t reserved;
+} rb_run;
+
+typedef struct rb_out {
+    /* per-sample output, any layout expressible by two strides (elements), or NULL:
+     * field f of sample k of trajectory i at samples[k*sample_stride + f*field_stride + i]. */
+    double *samples;
+    int64_t sample_stride;   /* e.g. 8*n for [n_out][8][n] */
+    int64_t field_stride;    /* e.g. n */
+    int64_t n_out_capacity;  /* samples the buffer can hold (>= n_steps/out_stride + 1) */
+    /* per-trajectory summary; final_state is REQUIRED (it doubles as the in-place state),
+     * SoA [6][n]: the dense-output state at the impact time, or the last step's state. */
+    double *final_state;
+    int32_t *impact_step;    /* [n], -1 = none */
+    double *impact_time;     /* [n], NaN = none */
+    uint8_t *status;         /* [n] rb_traj_status (REQUIRED) */
+    int32_t *n_samples;      /* [n] valid samples of trajectory i (grid times not after the event), or NULL */
+} rb_out;
+
+/* Replaces SpacecraftModel.run_simulation (spacecraft_model.py:490-519; solve_ivp call :516)
+ * for ensembles.  Asynchronous on `stream` (see RB_FLAG_EARLY_EXIT). */
+int32_t rb_propagate(rb_ctx *ctx, const rb_in *in, const rb_run *run, const rb_out *out, void *stream);
+
+/* Launch statistics of the last rb_propagate on this context (host-side counters). */
+typedef struct rb_stats {
+    int64_t kernel_launches;     /* all kernels of the call */
+    int64_t propagate_launches;  /* launches of the step kernel */
+    int64_t steps_enqueued;      /* steps covered by those launches */
+    int64_t last_polled_live;    /* last live count the host saw (-1 if never polled) */
+    double propagate_ms;         /* sum of step-kernel durations (RB_FLAG_PROFILE only, else 0) */
+} rb_stats;
+int32_t rb_ctx_stats(const rb_ctx *ctx, rb_stats *out);
+
+/* ---- per-sample diagnostics: the dict of SpacecraftModel.equations_of_motion
+ * (spacecraft_model.py:472-480) for n given (t, y) pairs; used for additional_data
+ * (spacecraft_model.py:517-518).  t device [n]; y SoA [6][n]; out SoA [RB_DIAG_FIELDS][n]:
+ * a_total[3], a_grav[3], a_j2[3], a_moon[3], a_sun[3], a_drag[3], altitude, latitude_deg, rho, T. */
+#define RB_DIAG_FIELDS 22
+int32_t rb_equations_of_motion(rb_ctx *ctx, int64_t n, const double *t, const double *y, double epoch_jd,
+                               double gmst0, const double *cd, const double *area, const double *mass,
+                               double cd_scalar, double area_scalar, double mass_scalar, double *out,
+                               void *stream);
+
+/* ---- host-buffer convenience (the end-to-end call of a ctypes / cgo style binding) ----
+ * Everything is HOST memory (pinned memory from rb_host_alloc makes the copies asynchronous):
+ * y0 [n][6]; cd/area/mass [n] or NULL; samples [n_out][8][n] or NULL; final_state [n][6].
+ * Builds the time table, uploads, propagates, downloads, synchronises. */
+int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double *cd, const double *area,
+                          const double *mass, double cd_scalar, double area_scalar, double mass_scalar,
+                          double epoch_jd, double gmst0, double t0, double dt, const rb_run *run,
+                          double *samples, int64_t n_out_capacity, double *final_state,
+                          int32_t *impact_step, double *impact_time, uint8_t *status, int32_t *n_samples,
+                          int64_t *n_samples_used);
+void *rb_host_alloc(int64_t bytes); /* pinned host memory (cudaHostAlloc) or NULL */
+void rb_host_free(void *p);
+
+/* FP64 FMA peak probe used for the roofline denominator (MEASURED_PEAKS.json has no FP64
+ * figure): runs a register-resident DFMA kernel for about `ms` milliseconds on `stream`,
+ * returns achieved TFLOP/s (DFMA = 2 flop). */
+int32_t rb_fp64_peak_probe(rb_ctx *ctx, double ms, double *tflops_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REENTRY_B200_H */

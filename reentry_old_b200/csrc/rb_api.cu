@@ -1,0 +1,563 @@
+// rb_api.cu -- C ABI (include/reentry_b200.h) of the B200-native ensemble propagator.
+// Host orchestration: context + workspace, time-table build/upload, launch sequence of the
+// step kernel with live-list compaction between launches, lagged live-count polling,
+// impact refinement, host-buffer convenience path with overlapped sample download.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "rb_kernels.cuh"
+#include "reentry_b200.h"
+
+using namespace rb;
+
+#ifndef RB_BLOCK
+#define RB_BLOCK 256
+#endif
+#ifndef RB_MIN_BLOCKS
+#define RB_MIN_BLOCKS 2
+#endif
+
+struct rb_ctx {
+    int device = 0;
+    char err[512] = {0};
+    // time table
+    double *d_table = nullptr;
+    int64_t table_capacity = 0;  // entries allocated
+    int64_t table_steps = -1;    // steps covered
+    double t0 = 0, dt = 0;
+    // workspace
+    int32_t *d_live[2] = {nullptr, nullptr};
+    int32_t *d_block_counts = nullptr;
+    int32_t *d_n_live = nullptr;  // [0] live count, [1] fresh count (scratch), [2] edge-sample counter
+    int64_t ws_n = 0;
+    int32_t *h_poll = nullptr;  // pinned ring
+    cudaEvent_t poll_ev[8] = {};
+    bool events_ready = false;
+    // host-path device buffers (grow-only)
+    void *d_host_bufs[8] = {nullptr};
+    size_t d_host_bytes[8] = {0};
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t compute_stream = nullptr;
+    double *h_table = nullptr;  // pinned staging for the table
+    int64_t h_table_entries = 0;
+    rb_stats stats = {0, 0, 0, -1, 0.0};
+    std::vector<cudaEvent_t> prof_events;
+};
+
+static int32_t cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what) {
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s: %s", what, cudaGetErrorString(e));
+    return RB_ERR_CUDA;
+}
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);     \
+    } while (0)
+
+extern "C" {
+
+int32_t rb_abi_version(void) { return RB_ABI_VERSION; }
+
+const char *rb_strerror(int32_t code) {
+    switch (code) {
+        case RB_OK: return "ok";
+        case RB_ERR_INVALID_ARG: return "invalid argument";
+        case RB_ERR_CUDA: return "CUDA error (see rb_ctx_last_error)";
+        case RB_ERR_NO_TIME_TABLE: return "no time table staged (rb_ctx_set_time_table)";
+        case RB_ERR_TABLE_RANGE: return "run exceeds the staged time table";
+        case RB_ERR_NOMEM: return "out of memory";
+        case RB_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+const char *rb_ctx_last_error(const rb_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+int32_t rb_ctx_create(rb_ctx **out, int32_t device) {
+    if (!out) return RB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return RB_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return RB_ERR_INVALID_ARG;
+    rb_ctx *ctx = new (std::nothrow) rb_ctx();
+    if (!ctx) return RB_ERR_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n_live, 4 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_poll, 8 * sizeof(int32_t), cudaHostAllocDefault);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->poll_ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        ctx->events_ready = true;
+        e = cudaFuncSetAttribute(k_propagate<RB_BLOCK, RB_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)propagate_smem_bytes<RB_BLOCK>());
+    }
+    if (e != cudaSuccess) {
+        fprintf(stderr, "rb_ctx_create: %s\n", cudaGetErrorString(e));
+        delete ctx;
+        return RB_ERR_CUDA;
+    }
+    *out = ctx;
+    return RB_OK;
+}
+
+int32_t rb_ctx_destroy(rb_ctx *ctx) {
+    if (!ctx) return RB_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_table);
+    cudaFree(ctx->d_live[0]);
+    cudaFree(ctx->d_live[1]);
+    cudaFree(ctx->d_block_counts);
+    cudaFree(ctx->d_n_live);
+    cudaFreeHost(ctx->h_poll);
+    cudaFreeHost(ctx->h_table);
+    for (auto &b : ctx->d_host_bufs) cudaFree(b);
+    if (ctx->events_ready)
+        for (auto &ev : ctx->poll_ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->prof_events) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
+    delete ctx;
+    return RB_OK;
+}
+
+int32_t rb_ctx_stats(const rb_ctx *ctx, rb_stats *out) {
+    if (!ctx || !out) return RB_ERR_INVALID_ARG;
+    *out = ctx->stats;
+    return RB_OK;
+}
+
+// ------------------------------------------------------------------ time table
+int64_t rb_time_table_entries(int64_t n_steps) { return n_steps < 0 ? 0 : RB_STAGES_PER_STEP * n_steps + 1; }
+
+int32_t rb_build_time_table(double epoch_jd, double gmst0, double t0, double dt, int64_t n_steps, double *host_table,
+                            int32_t n_threads) {
+    if (!host_table || n_steps < 0 || !(dt > 0)) return RB_ERR_INVALID_ARG;
+    // stage times exactly as scipy forms them: t_{n+1} = t_n + h (rk.py t_new = t + h), t_n + C_s*h (rk.py:64)
+    const double C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+    std::vector<double> tn((size_t)n_steps + 1);
+    double t = t0;
+    for (int64_t n = 0; n <= n_steps; ++n) { tn[(size_t)n] = t; t = t + dt; }
+    const int64_t n_entries = rb_time_table_entries(n_steps);
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(n_threads) if (n_entries > 512)
+#endif
+    for (int64_t e = 0; e < n_entries; ++e) {
+        double te;
+        if (e == 0) te = tn[0];
+        else {
+            const int64_t n = (e - 1) / RB_STAGES_PER_STEP;
+            const int s = (int)((e - 1) % RB_STAGES_PER_STEP) + 1;
+            te = (s == 5) ? tn[(size_t)n + 1] : tn[(size_t)n] + C[s] * dt;
+        }
+        time_entry(te, epoch_jd, gmst0, host_table + e * ENTRY_DOUBLES);
+    }
+    (void)n_threads;
+    return RB_OK;
+}
+
+int32_t rb_ctx_set_time_table(rb_ctx *ctx, const double *host_table, int64_t n_steps, double t0, double dt,
+                              void *stream) {
+    if (!ctx || !host_table || n_steps < 0) return RB_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n_entries = rb_time_table_entries(n_steps);
+    if (n_entries > ctx->table_capacity) {
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(ctx->d_table);
+        ctx->d_table = nullptr;
+        ctx->table_capacity = 0;
+        CK(cudaMalloc(&ctx->d_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double)));
+        ctx->table_capacity = n_entries;
+    }
+    CK(cudaMemcpyAsync(ctx->d_table, host_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double),
+                       cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    ctx->table_steps = n_steps;
+    ctx->t0 = t0;
+    ctx->dt = dt;
+    return RB_OK;
+}
+
+// ------------------------------------------------------------------ initial states
+int32_t rb_initial_states(rb_ctx *ctx, int64_t n, const double *v, const double *lat, const double *lon,
+                          const double *alt, const double *azimuth, const double *gamma, double gmst, double *y0,
+                          int64_t y0_traj_stride, int64_t y0_comp_stride, void *stream) {
+    if (!ctx || n < 0 || !v || !lat || !lon || !alt || !azimuth || !gamma || !y0) return RB_ERR_INVALID_ARG;
+    if (n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int B = 256;
+    k_initial_states<<<(unsigned)((n + B - 1) / B), B, 0, (cudaStream_t)stream>>>(n, v, lat, lon, alt, azimuth, gamma, gmst,
+                                                                                 y0, y0_traj_stride, y0_comp_stride);
+    CK(cudaGetLastError());
+    return RB_OK;
+}
+
+int32_t rb_equations_of_motion(rb_ctx *ctx, int64_t n, const double *t, const double *y, double epoch_jd, double gmst0,
+                               const double *cd, const double *area, const double *mass, double cd_scalar,
+                               double area_scalar, double mass_scalar, double *out, void *stream) {
+    if (!ctx || n < 0 || !t || !y || !out) return RB_ERR_INVALID_ARG;
+    if (n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    k_eom<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, t, y, epoch_jd, gmst0, cd, area, mass,
+                                                                         cd_scalar, area_scalar, mass_scalar, out);
+    CK(cudaGetLastError());
+    return RB_OK;
+}
+
+// ------------------------------------------------------------------ propagation
+static int32_t ensure_workspace(rb_ctx *ctx, int64_t n, cudaStream_t stream) {
+    if (n <= ctx->ws_n) return RB_OK;
+    CK(cudaStreamSynchronize(stream));
+    cudaFree(ctx->d_live[0]); cudaFree(ctx->d_live[1]); cudaFree(ctx->d_block_counts);
+    ctx->d_live[0] = ctx->d_live[1] = ctx->d_block_counts = nullptr;
+    ctx->ws_n = 0;
+    CK(cudaMalloc(&ctx->d_live[0], (size_t)n * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_live[1], (size_t)n * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_block_counts, (size_t)((n + COMPACT_BLOCK - 1) / COMPACT_BLOCK + 1) * sizeof(int32_t)));
+    ctx->ws_n = n;
+    return RB_OK;
+}
+
+// Called after the launch that completed `steps_done` steps of the run has been enqueued.
+struct LaunchHook {
+    virtual void after_launch(int64_t steps_done, cudaStream_t stream) = 0;
+    virtual ~LaunchHook() {}
+};
+
+static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, const rb_out *out, cudaStream_t stream,
+                              LaunchHook *hook, int64_t *steps_done_out) {
+    if (!ctx || !in || !run || !out) return RB_ERR_INVALID_ARG;
+    const int64_t n = in->n;
+    if (n < 0 || n > 0x7fffffffLL) return RB_ERR_INVALID_ARG;
+    if (!in->y0 || !out->final_state || !out->status || !out->impact_step) return RB_ERR_INVALID_ARG;
+    if (run->n_steps < 0 || run->first_step < 0 || run->out_stride < 1 || run->out_stride > 0x7fffffffLL)
+        return RB_ERR_INVALID_ARG;
+    if (ctx->table_steps < 0) return RB_ERR_NO_TIME_TABLE;
+    if (run->first_step + run->n_steps > ctx->table_steps) return RB_ERR_TABLE_RANGE;
+    if (out->samples && out->n_out_capacity < run->n_steps / run->out_stride + 1) return RB_ERR_INVALID_ARG;
+    ctx->stats = rb_stats{0, 0, 0, -1, 0.0};
+    if (steps_done_out) *steps_done_out = 0;
+    if (n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    int32_t rc = ensure_workspace(ctx, n, stream);
+    if (rc != RB_OK) return rc;
+
+    const int64_t spl = run->steps_per_launch > 0 ? run->steps_per_launch : 32;
+    const bool compact = (run->flags & RB_FLAG_COMPACT) != 0;
+    const bool early = (run->flags & RB_FLAG_EARLY_EXIT) != 0;
+    const bool profile = (run->flags & RB_FLAG_PROFILE) != 0;
+    size_t prof_used = 0;
+    auto prof_event = [&]() -> cudaEvent_t {
+        if (prof_used == ctx->prof_events.size()) {
+            cudaEvent_t ev = nullptr;
+            cudaEventCreate(&ev);
+            ctx->prof_events.push_back(ev);
+        }
+        return ctx->prof_events[prof_used++];
+    };
+
+    InitParams ip{};
+    ip.y0 = in->y0; ip.y0_traj_stride = in->y0_traj_stride; ip.y0_comp_stride = in->y0_comp_stride;
+    ip.state = out->final_state; ip.n = n; ip.live = ctx->d_live[0]; ip.n_live = ctx->d_n_live;
+    ip.impact_step = out->impact_step; ip.impact_time = out->impact_time; ip.status = out->status;
+    ip.samples = out->samples; ip.sample_stride = out->sample_stride; ip.field_stride = out->field_stride;
+    k_init<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ip);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+
+    StepParams sp{};
+    sp.table = ctx->d_table; sp.out_stride = run->out_stride; sp.h = ctx->dt; sp.event_altitude = run->event_altitude;
+    sp.state = out->final_state; sp.n = n;
+    sp.cd = in->cd; sp.area = in->area; sp.mass = in->mass;
+    sp.cd_s = in->cd_scalar; sp.area_s = in->area_scalar; sp.mass_s = in->mass_scalar;
+    sp.n_live = ctx->d_n_live;
+    sp.samples = out->samples; sp.sample_stride = out->sample_stride; sp.field_stride = out->field_stride;
+    sp.impact_step = out->impact_step; sp.status = out->status;
+
+    int cur = 0;               // live list in use
+    int64_t live_bound = n;    // host-side upper bound of the live count
+    int64_t done = 0;
+    int64_t launch_idx = 0;
+    const size_t smem = propagate_smem_bytes<RB_BLOCK>();
+    while (done < run->n_steps) {
+        if (early && launch_idx >= 2) {  // look at the live count published 2 launches ago
+            const int slot = (int)((launch_idx - 2) & 7);
+            CK(cudaEventSynchronize(ctx->poll_ev[slot]));
+            const int32_t seen = ctx->h_poll[slot];
+            ctx->stats.last_polled_live = seen;
+            live_bound = std::min<int64_t>(live_bound, seen);
+            if (seen == 0) break;
+        }
+        const int64_t steps = std::min<int64_t>(spl, run->n_steps - done);
+        sp.table_step0 = run->first_step + done;
+        sp.run_step0 = done;
+        sp.n_launch_steps = (int)steps;
+        sp.live = ctx->d_live[cur];
+        const unsigned grid = (unsigned)((live_bound + RB_BLOCK - 1) / RB_BLOCK);
+        if (profile) CK(cudaEventRecord(prof_event(), stream));
+        k_propagate<RB_BLOCK, RB_MIN_BLOCKS><<<grid, RB_BLOCK, smem, stream>>>(sp);
+        CK(cudaGetLastError());
+        if (profile) CK(cudaEventRecord(prof_event(), stream));
+        ctx->stats.kernel_launches++;
+        ctx->stats.propagate_launches++;
+        ctx->stats.steps_enqueued += steps;
+        done += steps;
+        if ((compact || early) && done < run->n_steps) {
+            const unsigned cgrid = (unsigned)((live_bound + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
+            k_count_live<<<cgrid, COMPACT_BLOCK, 0, stream>>>(ctx->d_live[cur], ctx->d_n_live, out->status, ctx->d_block_counts);
+            k_scan_blocks<<<1, 1024, 0, stream>>>(ctx->d_block_counts, (int)cgrid, ctx->d_n_live + 1);
+            ctx->stats.kernel_launches += 2;
+            if (compact) {
+                k_scatter_live<<<cgrid, COMPACT_BLOCK, 0, stream>>>(ctx->d_live[cur], ctx->d_n_live, out->status,
+                                                                    ctx->d_block_counts, ctx->d_live[cur ^ 1]);
+                CK(cudaMemcpyAsync(ctx->d_n_live, ctx->d_n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+                ctx->stats.kernel_launches++;
+                cur ^= 1;
+            }
+            CK(cudaGetLastError());
+            if (early) {
+                const int slot = (int)(launch_idx & 7);
+                CK(cudaMemcpyAsync(&ctx->h_poll[slot], ctx->d_n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+                CK(cudaEventRecord(ctx->poll_ev[slot], stream));
+            }
+        }
+        if (hook) hook->after_launch(done, stream);
+        ++launch_idx;
+    }
+
+    RefineParams rp{};
+    rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.event_altitude = run->event_altitude;
+    rp.state = out->final_state; rp.n = n;
+    rp.cd = in->cd; rp.area = in->area; rp.mass = in->mass;
+    rp.cd_s = in->cd_scalar; rp.area_s = in->area_scalar; rp.mass_s = in->mass_scalar;
+    rp.impact_step = out->impact_step; rp.impact_time = out->impact_time; rp.status = out->status;
+    rp.n_samples = out->n_samples;
+    rp.samples = out->samples; rp.sample_stride = out->sample_stride; rp.field_stride = out->field_stride;
+    rp.out_stride = run->out_stride; rp.run_first_step = run->first_step; rp.run_n_steps = run->n_steps;
+    rp.refine = (run->flags & RB_FLAG_NO_REFINE) ? 0 : 1;
+    rp.edge_count = ctx->d_n_live + 2;
+    CK(cudaMemsetAsync(ctx->d_n_live + 2, 0, sizeof(int32_t), stream));
+    k_refine<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(rp);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    if (steps_done_out) *steps_done_out = done;
+    if (profile) {
+        CK(cudaStreamSynchronize(stream));
+        double ms = 0.0;
+        for (size_t k = 0; k + 1 < prof_used; k += 2) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, ctx->prof_events[k], ctx->prof_events[k + 1]));
+            ms += t;
+        }
+        ctx->stats.propagate_ms = ms;
+    }
+    return RB_OK;
+}
+
+int32_t rb_propagate(rb_ctx *ctx, const rb_in *in, const rb_run *run, const rb_out *out, void *stream) {
+    return propagate_impl(ctx, in, run, out, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------ host-buffer path
+static int32_t host_buf(rb_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes > ctx->d_host_bytes[slot]) {
+        cudaFree(ctx->d_host_bufs[slot]);
+        ctx->d_host_bufs[slot] = nullptr;
+        ctx->d_host_bytes[slot] = 0;
+        CK(cudaMalloc(&ctx->d_host_bufs[slot], bytes));
+        ctx->d_host_bytes[slot] = bytes;
+    }
+    *out = ctx->d_host_bufs[slot];
+    return RB_OK;
+}
+
+__global__ void k_fill_nan(double *p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = nan("");
+}
+
+// transposes SoA [6][n] -> AoS [n][6] for the host-facing final_state
+__global__ void k_soa_to_aos6(const double *soa, double *aos, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) aos[i * 6 + c] = soa[c * n + i];
+}
+
+struct SampleDownloader : LaunchHook {
+    rb_ctx *ctx;
+    const double *d_samples;
+    double *h_samples;
+    int64_t n, out_stride, rows_copied = 0;
+    cudaStream_t copy_stream;
+    cudaEvent_t ev;
+    cudaError_t err = cudaSuccess;
+    void after_launch(int64_t steps_done, cudaStream_t stream) override {
+        // rows k <= steps_done/out_stride are final once this launch has finished
+        const int64_t rows_ready = steps_done / out_stride + 1;
+        if (rows_ready <= rows_copied) return;
+        cudaError_t e = cudaEventRecord(ev, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, ev, 0);
+        const size_t row = (size_t)RB_SAMPLE_FIELDS * n * sizeof(double);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync((char *)h_samples + rows_copied * row, (const char *)d_samples + rows_copied * row,
+                                (size_t)(rows_ready - rows_copied) * row, cudaMemcpyDeviceToHost, copy_stream);
+        if (e != cudaSuccess) err = e;
+        rows_copied = rows_ready;
+    }
+};
+
+int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double *cd, const double *area,
+                          const double *mass, double cd_scalar, double area_scalar, double mass_scalar, double epoch_jd,
+                          double gmst0, double t0, double dt, const rb_run *run, double *samples, int64_t n_out_capacity,
+                          double *final_state, int32_t *impact_step, double *impact_time, uint8_t *status,
+                          int32_t *n_samples, int64_t *n_samples_used) {
+    if (!ctx || !run || n < 0 || !y0 || !final_state || !impact_step || !impact_time || !status) return RB_ERR_INVALID_ARG;
+    if (run->first_step != 0) return RB_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->compute_stream;
+    const int64_t n_out = run->n_steps / run->out_stride + 1;
+    if (samples && n_out_capacity < n_out) return RB_ERR_INVALID_ARG;
+    if (n == 0) { if (n_samples_used) *n_samples_used = 0; return RB_OK; }
+
+    // time table: build on the host (all cores), stage through pinned memory
+    const int64_t n_entries = rb_time_table_entries(run->n_steps);
+    if (n_entries > ctx->h_table_entries) {
+        cudaFreeHost(ctx->h_table);
+        ctx->h_table = nullptr; ctx->h_table_entries = 0;
+        CK(cudaHostAlloc(&ctx->h_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double), cudaHostAllocDefault));
+        ctx->h_table_entries = n_entries;
+    }
+    CK(cudaStreamSynchronize(cs));  // previous call may still read the pinned table
+    int32_t rc = rb_build_time_table(epoch_jd, gmst0, t0, dt, run->n_steps, ctx->h_table, 0);
+    if (rc != RB_OK) return rc;
+    rc = rb_ctx_set_time_table(ctx, ctx->h_table, run->n_steps, t0, dt, cs);
+    if (rc != RB_OK) return rc;
+
+    void *d_y0, *d_state, *d_cam = nullptr, *d_istep, *d_itime, *d_status, *d_ns, *d_samples = nullptr;
+    if ((rc = host_buf(ctx, 0, (size_t)n * 6 * 8, &d_y0))) return rc;
+    if ((rc = host_buf(ctx, 1, (size_t)n * 6 * 8 * 2, &d_state))) return rc;  // SoA state + AoS transpose
+    if ((rc = host_buf(ctx, 2, (size_t)n * 3 * 8, &d_cam))) return rc;
+    if ((rc = host_buf(ctx, 3, (size_t)n * 4, &d_istep))) return rc;
+    if ((rc = host_buf(ctx, 4, (size_t)n * 8, &d_itime))) return rc;
+    if ((rc = host_buf(ctx, 5, (size_t)n, &d_status))) return rc;
+    if ((rc = host_buf(ctx, 6, (size_t)n * 4, &d_ns))) return rc;
+    const size_t row = (size_t)RB_SAMPLE_FIELDS * n * sizeof(double);
+    if (samples) {
+        if ((rc = host_buf(ctx, 7, (size_t)n_out * row, &d_samples))) return rc;
+        const int64_t cnt = n_out * RB_SAMPLE_FIELDS * n;
+        k_fill_nan<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>((double *)d_samples, cnt);
+    }
+    CK(cudaMemcpyAsync(d_y0, y0, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, cs));
+    double *d_cd = nullptr, *d_area = nullptr, *d_mass = nullptr;
+    if (cd) { d_cd = (double *)d_cam; CK(cudaMemcpyAsync(d_cd, cd, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+    if (area) { d_area = (double *)d_cam + n; CK(cudaMemcpyAsync(d_area, area, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+    if (mass) { d_mass = (double *)d_cam + 2 * n; CK(cudaMemcpyAsync(d_mass, mass, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+
+    rb_in in{};
+    in.n = n; in.y0 = (const double *)d_y0; in.y0_traj_stride = 6; in.y0_comp_stride = 1;
+    in.cd = d_cd; in.area = d_area; in.mass = d_mass;
+    in.cd_scalar = cd_scalar; in.area_scalar = area_scalar; in.mass_scalar = mass_scalar;
+    rb_out out{};
+    out.samples = (double *)d_samples; out.sample_stride = RB_SAMPLE_FIELDS * n; out.field_stride = n;
+    out.n_out_capacity = n_out;
+    out.final_state = (double *)d_state; out.impact_step = (int32_t *)d_istep; out.impact_time = (double *)d_itime;
+    out.status = (uint8_t *)d_status; out.n_samples = (int32_t *)d_ns;
+
+    SampleDownloader dl;
+    dl.ctx = ctx; dl.d_samples = (const double *)d_samples; dl.h_samples = samples; dl.n = n;
+    dl.out_stride = run->out_stride; dl.copy_stream = ctx->copy_stream;
+    cudaEvent_t ev = nullptr;
+    if (samples) { CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); dl.ev = ev; }
+    rb_run r2 = *run;
+    r2.flags |= RB_FLAG_EARLY_EXIT;
+    int64_t steps_done = 0;
+    rc = propagate_impl(ctx, &in, &r2, &out, cs, samples ? &dl : nullptr, &steps_done);
+    if (rc == RB_OK) {
+        double *d_aos = (double *)d_state + 6 * n;
+        k_soa_to_aos6<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>((const double *)d_state, d_aos, n);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(final_state, d_aos, (size_t)n * 6 * 8, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(impact_step, d_istep, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(impact_time, d_itime, (size_t)n * 8, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && n_samples) e = cudaMemcpyAsync(n_samples, d_ns, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+        int32_t edge = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&edge, ctx->d_n_live + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && samples) {
+            dl.after_launch(steps_done, cs);  // rows not yet sent
+            if (dl.err != cudaSuccess) e = dl.err;
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+        if (e == cudaSuccess && samples && edge > 0) {
+            // a grid sample coincided with an event time and was added by k_refine after its row had
+            // been sent (measure-zero case): send the rows again
+            e = cudaMemcpyAsync(samples, d_samples, (size_t)dl.rows_copied * row, cudaMemcpyDeviceToHost, cs);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "rb_propagate_host download");
+    }
+    if (ev) cudaEventDestroy(ev);
+    if (n_samples_used) *n_samples_used = samples ? dl.rows_copied : 0;
+    return rc;
+}
+
+void *rb_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void rb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ FP64 peak probe
+int32_t rb_fp64_peak_probe(rb_ctx *ctx, double ms, double *tflops_out, void *stream) {
+    if (!ctx || !tflops_out) return RB_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    double *sink;
+    CK(cudaMalloc(&sink, 8));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = prop.multiProcessorCount * 8, block = 256;
+    int iters = 2000;
+    double best = 0.0, elapsed_total = 0.0;
+    k_dfma_peak<<<grid, block, 0, s>>>(sink, 200, 1.0);  // warm-up
+    for (int rep = 0; rep < 50 && elapsed_total < ms; ++rep) {
+        CK(cudaEventRecord(a, s));
+        k_dfma_peak<<<grid, block, 0, s>>>(sink, iters, 1.0 + rep);
+        CK(cudaEventRecord(b, s));
+        CK(cudaEventSynchronize(b));
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, a, b));
+        const double flop = 2.0 * DFMA_PER_THREAD_ITER * (double)iters * grid * block;
+        best = std::max(best, flop / (t * 1e-3) / 1e12);
+        elapsed_total += t;
+        if (t < 5.0f) iters *= 2;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops_out = best;
+    return RB_OK;
+}
+
+}  // extern "C"

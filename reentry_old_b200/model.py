@@ -1,0 +1,351 @@
+"""Host-side mirror of the reference's spacecraft-model call surface for the propagation path.
+
+`SpacecraftModel` keeps the names, argument meaning and result layout of
+`/root/reference/spacecraft_model.py:392-519` (constructor :393, get_initial_state :412,
+equations_of_motion :437, run_simulation :490) and adds the ensemble entry point
+`run_ensemble`.  Every number is produced by the sm_100a kernels behind the C ABI
+(include/reentry_b200.h); torch is used only for device memory and streams.  There is no
+CPU fallback: without a CUDA device or without the built library the calls raise.
+
+Fixed-step contract: the reference integrates with scipy's adaptive
+RK45; this path integrates with the same Dormand-Prince tableau at a FIXED step (the spacing
+of `t_eval`, or `max_step`), which is the reference's own stepper with step-size control
+switched off.  `sim_type` other than 'RK45' raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+
+DEFAULT_EPOCH_JD = 2460310.5  # Time('2024-01-01 00:00:00').jd, the reference's default (spacecraft_model.py:393)
+EARTH_R = 6378137.0
+
+
+class Epoch:
+    """Anything with `.jd` works as `epoch` (the reference passes an astropy Time)."""
+
+    def __init__(self, jd: float = DEFAULT_EPOCH_JD):
+        self.jd = float(jd)
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise L.ReentryB200Error("no CUDA device: the B200 propagation path has no CPU fallback")
+    return torch
+
+
+class DeviceContext:
+    """One rb_ctx per (process, device)."""
+
+    _cache: dict = {}
+
+    def __init__(self, device: int):
+        self.lib = L.load()
+        self.device = int(device)
+        h = L.vp()
+        L.check(self.lib.rb_ctx_create(C.byref(h), self.device), None, "rb_ctx_create")
+        self.handle = h
+        self.table_key = None
+
+    @classmethod
+    def get(cls, device: Optional[int] = None) -> "DeviceContext":
+        torch = _torch()
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device(device).index if not isinstance(device, int) else device
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    def check(self, rc, what=""):
+        L.check(rc, self.handle, what)
+
+    def close(self):
+        if self.handle:
+            self.lib.rb_ctx_destroy(self.handle)
+            self.handle = None
+            self._cache.pop(self.device, None)
+
+    # -- time table -------------------------------------------------------------------
+    def stage_time_table(self, epoch_jd, gmst0, t0, dt, n_steps, stream_ptr, n_threads=0):
+        key = (float(epoch_jd), float(gmst0), float(t0), float(dt))
+        if self.table_key is not None and self.table_key[:4] == key and self.table_key[4] >= n_steps:
+            return
+        torch = _torch()
+        n_entries = self.lib.rb_time_table_entries(n_steps)
+        host = torch.empty(n_entries * L.RB_TABLE_ENTRY_DOUBLES, dtype=torch.float64).pin_memory()
+        self.check(self.lib.rb_build_time_table(epoch_jd, gmst0, t0, dt, n_steps, host.data_ptr(), n_threads),
+                   "rb_build_time_table")
+        self.check(self.lib.rb_ctx_set_time_table(self.handle, host.data_ptr(), n_steps, t0, dt, stream_ptr),
+                   "rb_ctx_set_time_table")
+        torch.cuda.current_stream(self.device).synchronize()  # pinned staging buffer is released below
+        self.table_key = key + (int(n_steps),)
+
+    def stats(self):
+        s = L.RbStats()
+        self.check(self.lib.rb_ctx_stats(self.handle, C.byref(s)))
+        return dict(kernel_launches=s.kernel_launches, propagate_launches=s.propagate_launches,
+                    steps_enqueued=s.steps_enqueued, last_polled_live=s.last_polled_live,
+                    propagate_ms=s.propagate_ms)
+
+    def fp64_peak_tflops(self, ms=200.0):
+        torch = _torch()
+        out = L.f64(0)
+        self.check(self.lib.rb_fp64_peak_probe(self.handle, float(ms), C.byref(out),
+                                               torch.cuda.current_stream(self.device).cuda_stream))
+        return out.value
+
+
+@dataclass
+class EnsembleResult:
+    """Device-resident result of `run_ensemble` (torch tensors on the GPU unless noted)."""
+    t: np.ndarray                      # [n_out] sample times (host)
+    samples: Optional["object"]        # [n_out, 8, N] f64: x,y,z,vx,vy,vz,altitude,speed (NaN after the event)
+    final_state: "object"              # [6, N]
+    impact_step: "object"              # [N] int32, -1 = none
+    impact_time: "object"              # [N] f64, NaN = none
+    status: "object"                   # [N] uint8: 0 alive, 1 impacted, 2 non-finite
+    n_samples: "object"                # [N] int32
+    dt: float = 0.0
+    out_stride: int = 1
+    n_steps: int = 0
+    stats: dict = field(default_factory=dict)
+
+    @property
+    def y(self):          # [N, 6, n_out] view (sol.y of trajectory i is y[i])
+        return self.samples[:, :6, :].permute(2, 1, 0)
+
+    @property
+    def altitude(self):   # [N, n_out]
+        return self.samples[:, 6, :].transpose(0, 1)
+
+    @property
+    def speed(self):      # [N, n_out]
+        return self.samples[:, 7, :].transpose(0, 1)
+
+    @property
+    def t_events(self):   # impact times of the trajectories that hit, host
+        it = self.impact_time.cpu().numpy()
+        return it[~np.isnan(it)]
+
+
+class OdeResultLike(dict):
+    """scipy OdeResult stand-in (attribute access), plus `.additional_data` as the reference adds (:518)."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+
+
+class SpacecraftModel:
+    def __init__(self, Cd=2.2, A=20.0, m=500.0, epoch=None, gmst0=0.0, sim_type="RK45",
+                 material=(233, 1, 1, 0.1), dt=10, iter_fact=2, device=None):
+        # same attributes as spacecraft_model.py:394-410
+        self.Cd = Cd
+        self.A = A
+        self.height = float(np.sqrt(self.A / np.pi) * 1.315)
+        self.m = m
+        if epoch is None:
+            epoch = Epoch()
+        self.epoch = float(epoch.jd) if hasattr(epoch, "jd") else float(epoch)
+        self.start_time = time.time()
+        self.A_over_m = self.A / self.m
+        self.gmst0 = float(gmst0)  # radians in use (app.py:109)
+        self.thickness = 0.1
+        self.sim_type = sim_type
+        self.mat = material
+        self.thermal_conductivity, self.specific_heat_capacity, self.emissivity, self.ablation_efficiency = material[:4]
+        self.dt = dt
+        self.iter_fact = iter_fact
+        self.device = device
+
+    # ------------------------------------------------------------------------- plumbing
+    def _ctx(self) -> DeviceContext:
+        return DeviceContext.get(self.device)
+
+    def _dev(self, x, n=None):
+        """numpy / scalar / tensor -> contiguous float64 CUDA tensor (broadcast to n if given)."""
+        torch = _torch()
+        ctx = self._ctx()
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(np.asarray(x, dtype=np.float64))
+        x = x.to(device=f"cuda:{ctx.device}", dtype=torch.float64)
+        if n is not None:
+            x = x.reshape(-1) if x.ndim else x.reshape(1)
+            if x.numel() == 1 and n != 1:
+                x = x.expand(n)
+            if x.numel() != n:
+                raise ValueError(f"expected {n} values, got {x.numel()}")
+        return x.contiguous()
+
+    # --------------------------------------------------------------- get_initial_state
+    def get_initial_state(self, v, lat, lon, alt, azimuth, gamma, gmst=0.0):
+        """spacecraft_model.py:412-435.  Scalars -> float64[6] (numpy, like the reference);
+        arrays of length N -> CUDA tensor [N, 6]."""
+        scalar = all(np.ndim(a) == 0 for a in (v, lat, lon, alt, azimuth, gamma))
+        y0 = self.get_initial_states(v, lat, lon, alt, azimuth, gamma, gmst)
+        return y0[0].cpu().numpy() if scalar else y0
+
+    def get_initial_states(self, v, lat, lon, alt, azimuth, gamma, gmst=0.0):
+        torch = _torch()
+        ctx = self._ctx()
+        n = max(int(np.size(a)) if not hasattr(a, "numel") else int(a.numel()) for a in (v, lat, lon, alt, azimuth, gamma))
+        args = [self._dev(a, n) for a in (v, lat, lon, alt, azimuth, gamma)]
+        y0 = torch.empty((n, 6), dtype=torch.float64, device=args[0].device)
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.check(ctx.lib.rb_initial_states(ctx.handle, n, *[a.data_ptr() for a in args], float(gmst),
+                                            y0.data_ptr(), 6, 1, stream), "rb_initial_states")
+        return y0
+
+    # ------------------------------------------------------------- equations_of_motion
+    def equations_of_motion_batch(self, t, y, Cd=None, A=None, m=None):
+        """Device evaluation of the RHS dict for N (t, y) pairs.  t [N]; y [N,6] -> dict of CUDA tensors."""
+        torch = _torch()
+        ctx = self._ctx()
+        y = self._dev(y)
+        y = y.reshape(-1, 6)
+        n = y.shape[0]
+        t = self._dev(t, n)
+        ysoa = y.t().contiguous()
+        out = torch.empty((L.RB_DIAG_FIELDS, n), dtype=torch.float64, device=y.device)
+        arr = [None if a is None else self._dev(a, n) for a in (Cd, A, m)]
+        ptr = [0 if a is None else a.data_ptr() for a in arr]
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.check(ctx.lib.rb_equations_of_motion(ctx.handle, n, t.data_ptr(), ysoa.data_ptr(), self.epoch, self.gmst0,
+                                                 ptr[0], ptr[1], ptr[2], float(self.Cd), float(self.A), float(self.m),
+                                                 out.data_ptr(), stream), "rb_equations_of_motion")
+        o = out
+        return {
+            "velocity": y[:, 3:6],
+            "acceleration": o[0:3].t(), "gravitational_acceleration": o[3:6].t(), "J2_acceleration": o[6:9].t(),
+            "moon_acceleration": o[9:12].t(), "sun_acceleration": o[12:15].t(), "drag_acceleration": o[15:18].t(),
+            "altitude": o[18], "latitude": o[19], "density": o[20], "temperature": o[21],
+        }
+
+    def equations_of_motion(self, t, y):
+        """spacecraft_model.py:437-487 for one state: dict of numpy values (thermal entries are
+        outside this path)."""
+        d = self.equations_of_motion_batch(np.array([float(t)]), np.asarray(y, dtype=np.float64).reshape(1, 6))
+        out = {}
+        for k, v_ in d.items():
+            a = v_.cpu().numpy()
+            out[k] = a[0].copy() if a.ndim == 2 else float(a[0])
+        return out
+
+    # ------------------------------------------------------------------- run_ensemble
+    def run_ensemble(self, y0, t0=0.0, dt=1.0, n_steps=0, out_stride=1, Cd=None, A=None, m=None,
+                     store_samples=True, steps_per_launch=0, compact=True, early_exit=True, refine=True,
+                     event_altitude=1000.0, table_threads=0, profile=False) -> EnsembleResult:
+        """Propagate N independent initial states y0[N,6] for up to n_steps fixed steps of dt.
+
+        Per-trajectory Cd / A / m may be given as arrays [N]; otherwise the model's scalars apply.
+        Samples are stored every `out_stride` steps as [n_out, 8, N] (SoA, coalesced).
+        """
+        torch = _torch()
+        ctx = self._ctx()
+        if self.sim_type != "RK45":
+            raise NotImplementedError("only the RK45 (Dormand-Prince) tableau is implemented on this path")
+        if not (dt > 0) or n_steps < 0 or out_stride < 1:
+            raise ValueError("need dt > 0, n_steps >= 0, out_stride >= 1")
+        if not (isinstance(y0, torch.Tensor) and y0.is_cuda and y0.dtype == torch.float64 and y0.ndim == 2
+                and y0.device.index == ctx.device):
+            y0 = self._dev(y0)   # strided CUDA tensors (e.g. SoA views) are passed as they are
+        if y0.ndim == 1:
+            y0 = y0.reshape(1, 6)
+        if y0.ndim != 2 or y0.shape[1] != 6:
+            raise ValueError("y0 must be [N, 6]")
+        n = y0.shape[0]
+        dev = y0.device
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.stage_time_table(self.epoch, self.gmst0, float(t0), float(dt), int(n_steps), stream, table_threads)
+        n_out = n_steps // out_stride + 1
+        samples = torch.full((n_out, L.RB_SAMPLE_FIELDS, n), float("nan"), dtype=torch.float64, device=dev) \
+            if store_samples else None
+        final_state = torch.empty((6, n), dtype=torch.float64, device=dev)
+        impact_step = torch.empty(n, dtype=torch.int32, device=dev)
+        impact_time = torch.empty(n, dtype=torch.float64, device=dev)
+        status = torch.empty(n, dtype=torch.uint8, device=dev)
+        n_samples = torch.empty(n, dtype=torch.int32, device=dev)
+        arr = [None if a is None else self._dev(a, n) for a in (Cd, A, m)]
+        rin = L.RbIn(n=n, y0=y0.data_ptr(), y0_traj_stride=y0.stride(0), y0_comp_stride=y0.stride(1),
+                     cd=None if arr[0] is None else arr[0].data_ptr(),
+                     area=None if arr[1] is None else arr[1].data_ptr(),
+                     mass=None if arr[2] is None else arr[2].data_ptr(),
+                     cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
+        flags = (L.RB_FLAG_COMPACT if compact else 0) | (L.RB_FLAG_EARLY_EXIT if early_exit else 0) | \
+                (0 if refine else L.RB_FLAG_NO_REFINE) | (L.RB_FLAG_PROFILE if profile else 0)
+        run = L.RbRun(first_step=0, n_steps=int(n_steps), out_stride=int(out_stride),
+                      steps_per_launch=int(steps_per_launch), event_altitude=float(event_altitude), flags=flags)
+        out = L.RbOut(samples=None if samples is None else samples.data_ptr(),
+                      sample_stride=L.RB_SAMPLE_FIELDS * n, field_stride=n, n_out_capacity=n_out,
+                      final_state=final_state.data_ptr(), impact_step=impact_step.data_ptr(),
+                      impact_time=impact_time.data_ptr(), status=status.data_ptr(), n_samples=n_samples.data_ptr())
+        if n > 0:
+            ctx.check(ctx.lib.rb_propagate(ctx.handle, C.byref(rin), C.byref(run), C.byref(out), stream), "rb_propagate")
+        t = float(t0) + float(dt) * out_stride * np.arange(n_out)
+        return EnsembleResult(t=t, samples=samples, final_state=final_state, impact_step=impact_step,
+                              impact_time=impact_time, status=status, n_samples=n_samples, dt=float(dt),
+                              out_stride=int(out_stride), n_steps=int(n_steps), stats=ctx.stats())
+
+    # ------------------------------------------------------------------ run_simulation
+    def run_simulation(self, t_span, y0, t_eval, progress_callback=None, max_step=None):
+        """spacecraft_model.py:490-519 for ONE trajectory, fixed-step contract.
+
+        `t_eval` must be a uniform grid starting at t_span[0] (the app builds
+        `np.arange(ts, tf, dt)`, app.py:171); the integration step is its spacing, or `max_step`
+        if given (the spacing must then be an integer multiple of it).  Returns an
+        OdeResult-like object: t [n], y [6, n] (grid samples not after the event, scipy t_eval
+        semantics), t_events = [array([impact time]) or empty, empty], y_events, status,
+        additional_data (dict of [n] / [n, 3] arrays, keys of :472-480).
+        """
+        t_eval = np.asarray(t_eval, dtype=np.float64)
+        t0, tf = float(t_span[0]), float(t_span[1])
+        if t_eval.ndim != 1 or t_eval.size < 1:
+            raise ValueError("t_eval must be a non-empty 1-D grid")
+        if t_eval.size > 1:
+            spacing = float(t_eval[1] - t_eval[0])
+            if not np.allclose(np.diff(t_eval), spacing, rtol=1e-9, atol=1e-12) or spacing <= 0:
+                raise ValueError("this path integrates at a fixed step: t_eval must be uniformly spaced")
+        else:
+            spacing = tf - t0
+        if abs(t_eval[0] - t0) > 1e-9 * max(1.0, abs(t0)):
+            raise ValueError("t_eval must start at t_span[0]")
+        h = float(max_step) if max_step else spacing
+        stride = int(round(spacing / h))
+        if stride < 1 or abs(stride * h - spacing) > 1e-9 * spacing:
+            raise ValueError("t_eval spacing must be an integer multiple of max_step")
+        n_steps = int(np.floor((tf - t0) / h + 1e-9))
+        res = self.run_ensemble(np.asarray(y0, dtype=np.float64).reshape(1, 6), t0=t0, dt=h, n_steps=n_steps,
+                                out_stride=stride, steps_per_launch=0)
+        n_valid = min(int(res.n_samples[0].item()), t_eval.size)
+        samples = res.samples[:n_valid, :, 0].cpu().numpy()       # [n, 8]
+        status = int(res.status[0].item())
+        te = float(res.impact_time[0].item())
+        sol = OdeResultLike()
+        sol.t = t_eval[:n_valid].copy()
+        sol.y = np.ascontiguousarray(samples[:, :6].T)
+        hit = status == L.TRAJ_IMPACTED
+        sol.t_events = [np.array([te]) if hit else np.array([]), np.array([])]
+        sol.y_events = [res.final_state[:, 0].cpu().numpy()[None, :] if hit else np.empty((0, 6)), np.empty((0, 6))]
+        sol.status = 1 if hit else (0 if status == L.TRAJ_ALIVE else -1)
+        sol.success = status != L.TRAJ_NONFINITE
+        sol.message = ("A termination event occurred." if hit else
+                       "The solver successfully reached the end of the integration interval." if sol.success
+                       else "Non-finite state encountered.")
+        steps_done = (int(res.impact_step[0].item()) if status != L.TRAJ_ALIVE else n_steps)
+        sol.nfev = 6 * steps_done + 1
+        sol.njev = 0
+        sol.nlu = 0
+        sol.sol = None
+        # additional_data: re-evaluate the RHS at every output sample, as the reference does (:517-518)
+        d = self.equations_of_motion_batch(sol.t, samples[:, :6]) if n_valid else {}
+        sol.additional_data = {k: v_.cpu().numpy().copy() for k, v_ in d.items()}
+        if progress_callback is not None:
+            progress_callback(1.0, time.time() - self.start_time)
+        return sol

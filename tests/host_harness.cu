@@ -1,0 +1,71 @@
+// TEST INFRASTRUCTURE -- compiles the product's __host__ __device__ physics (rb_physics.cuh,
+// time_entry of rb_kernels.cuh) for the HOST so that `-m "not gpu"` tests can check the same
+// source against the oracle without a GPU.  Never loaded by the product.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "rb_kernels.cuh"
+
+using namespace rb;
+
+static const double A_[7][6] = {RB_DP_A_ROWS};
+
+extern "C" {
+
+void hh_time_entry(double t, double epoch0, double gmst0, double *e) { time_entry(t, epoch0, gmst0, e); }
+
+void hh_acceleration(const double *e, const double *r, const double *v, double cd, double area, double mass, double *a,
+                     double *diag22) {
+    Body b{cd, area, mass};
+    RhsOut d;
+    acceleration<true>(e, r, v, b, a, &d);
+    if (diag22) {
+        for (int c = 0; c < 3; ++c) {
+            diag22[c] = a[c]; diag22[3 + c] = d.a_grav[c]; diag22[6 + c] = d.a_j2[c];
+            diag22[9 + c] = d.a_moon[c]; diag22[12 + c] = d.a_sun[c]; diag22[15 + c] = d.a_drag[c];
+        }
+        diag22[18] = d.altitude; diag22[19] = d.latitude_deg; diag22[20] = d.rho; diag22[21] = d.T;
+    }
+}
+
+double hh_geodetic_latitude_deg(double x, double y, double z) { return geodetic_latitude_deg(x, y, z); }
+double hh_density(double alt, double lat, double solar_time, double *T) { return density(alt, lat, solar_time, *T); }
+
+// Same stage arithmetic as k_propagate (fma chains, table entries), on the host, one trajectory.
+// table: [(5*n_steps+1)][16].  ys_out: [n_steps+1][6].  Returns the impact step or -1.
+int64_t hh_propagate(const double *table, const double *y0, double cd, double area, double mass, double h,
+                     int64_t n_steps, double event_altitude, double *ys_out) {
+    Body b{cd, area, mass};
+    double y[6], K[7][6], ys[6];
+    memcpy(y, y0, sizeof y);
+    memcpy(ys_out, y, sizeof y);
+    double g_old = event_g(y, event_altitude);
+    int k0 = 0;
+    for (int64_t n = 0; n < n_steps; ++n) {
+        for (int s = (n == 0 ? 0 : 1); s <= 6; ++s) {
+            const int slot = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
+            if (s == 0) memcpy(ys, y, sizeof y);
+            else {
+                double acc[6];
+                for (int c = 0; c < 6; ++c) acc[c] = A_[s][0] * K[k0][c];
+                for (int j = 1; j < s; ++j)
+                    for (int c = 0; c < 6; ++c) acc[c] = fma(A_[s][j], K[j][c], acc[c]);
+                for (int c = 0; c < 6; ++c) ys[c] = fma(acc[c], h, y[c]);
+            }
+            const int64_t e = 5 * n + ((s == 6) ? 5 : s);
+            double a[3];
+            acceleration<false>(table + e * 16, ys, ys + 3, b, a, nullptr);
+            K[slot][0] = ys[3]; K[slot][1] = ys[4]; K[slot][2] = ys[5];
+            K[slot][3] = a[0]; K[slot][4] = a[1]; K[slot][5] = a[2];
+        }
+        const double g_new = event_g(ys, event_altitude);
+        if (g_old >= 0.0 && g_new <= 0.0) return n + 1;
+        memcpy(y, ys, sizeof y);
+        g_old = g_new;
+        k0 = 6 - k0;
+        memcpy(ys_out + 6 * (n + 1), y, sizeof y);
+    }
+    return -1;
+}
+}

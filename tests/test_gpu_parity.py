@@ -1,0 +1,326 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(ctypes -> libreentry_b200.so); the CPU oracle and the golden vectors of the unmodified
+reference are the checkers.
+
+Tolerances (BASELINE.json north_star): per-step position <= 1e-9 relative AND < 1 m absolute,
+velocity <= 1e-9 relative, identical impact step except where the crossing is within 1e-6 m of
+the step boundary; impact time within 1e-7 s.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POS_REL, VEL_REL, POS_ABS, T_ABS = 1e-9, 1e-9, 1.0, 1e-7
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+
+    if not t.cuda.is_available():
+        pytest.skip("no GPU")
+    return t
+
+
+@pytest.fixture(scope="module")
+def Model(torch):
+    from reentry_old_b200 import SpacecraftModel
+
+    return SpacecraftModel
+
+
+def compare_states(got, ref, what=""):
+    """got/ref [..., 6] with identical NaN pattern."""
+    ok = ~np.isnan(ref[..., 0])
+    assert np.array_equal(ok, ~np.isnan(got[..., 0])), f"{what}: sample validity differs"
+    g, r = got[ok], ref[ok]
+    dpos = np.linalg.norm(g[:, :3] - r[:, :3], axis=1)
+    rel = dpos / np.linalg.norm(r[:, :3], axis=1)
+    relv = np.linalg.norm(g[:, 3:6] - r[:, 3:6], axis=1) / np.linalg.norm(r[:, 3:6], axis=1)
+    assert rel.max() <= POS_REL, (what, "pos rel", rel.max())
+    assert dpos.max() < POS_ABS, (what, "pos abs", dpos.max())
+    assert relv.max() <= VEL_REL, (what, "vel rel", relv.max())
+    return rel.max(), relv.max()
+
+
+def run_golden(Model, g, **kw):
+    m = Model(Cd=float(np.atleast_1d(g["Cd"])[0]), A=float(np.atleast_1d(g["A"])[0]), m=float(np.atleast_1d(g["m"])[0]),
+              epoch=float(g["epoch_jd"]), gmst0=float(g["gmst0"]))
+    per = {k: (g[key] if np.ndim(g[key]) else None) for k, key in (("Cd", "Cd"), ("A", "A"), ("m", "m"))}
+    stride = int(g["stride"]) if "stride" in g else 1
+    return m.run_ensemble(g["y0"].reshape(-1, 6), t0=float(g["t0"]), dt=float(g["dt"]), n_steps=int(g["n_steps"]),
+                          out_stride=stride, **per, **kw)
+
+
+def samples_np(res):
+    return res.samples.permute(2, 0, 1).cpu().numpy()  # [N, n_out, 8]
+
+
+# ------------------------------------------------------------------------------- leaves
+def test_initial_states_vs_oracle(Model, oracle):
+    rng = np.random.default_rng(3)
+    n = 2000
+    p = np.stack([rng.uniform(100, 9000, n), rng.uniform(-89.9, 89.9, n), rng.uniform(-180, 180, n),
+                  rng.uniform(0, 1e6, n), rng.uniform(0, 360, n), rng.uniform(-90, 90, n)], axis=1)
+    m = Model()
+    for gmst in (0.0, 1.25, 2000.5):
+        got = m.get_initial_states(*p.T, gmst=gmst).cpu().numpy()
+        ref = oracle.get_initial_states(*p.T, gmst)
+        assert np.max(np.linalg.norm(got[:, :3] - ref[:, :3], axis=1) / np.linalg.norm(ref[:, :3], axis=1)) < 1e-14
+        assert np.max(np.linalg.norm(got[:, 3:] - ref[:, 3:], axis=1) / np.linalg.norm(ref[:, 3:], axis=1)) < 1e-13
+    y = m.get_initial_state(7800, 0, 0, 120e3, 90, -1, gmst=0)   # scalar call surface of the reference
+    assert isinstance(y, np.ndarray) and y.shape == (6,) and y[0] == 6498137.0
+    assert np.allclose(y, [6498137.0, 0.0, 0.0, -136.12877021081138, 7798.812022219852, 4.77539509008172e-13],
+                       rtol=1e-14, atol=1e-12)
+
+
+def test_equations_of_motion_vs_golden(Model, golden_dir):
+    g = np.load(os.path.join(golden_dir, "rhs_random.npz"))
+    m = Model(Cd=float(g["Cd"]), A=float(g["A"]), m=float(g["m"]), epoch=float(g["epoch_jd"]), gmst0=float(g["gmst0"]))
+    d = m.equations_of_motion_batch(g["t"], g["y"])
+    for key in ("acceleration", "gravitational_acceleration", "J2_acceleration", "moon_acceleration",
+                "sun_acceleration", "drag_acceleration"):
+        got, ref = d[key].cpu().numpy(), g[key]
+        err = np.abs(got - ref).max(axis=1)
+        # 1e-12 of the term; the third-body terms are differences of ~6e-3 m/s^2 pieces (1e-17 floor)
+        assert np.all(err <= 1e-12 * np.linalg.norm(ref, axis=1) + 1e-17), (key, err.max())
+    assert np.array_equal(d["altitude"].cpu().numpy(), g["altitude"])
+    one = m.equations_of_motion(float(g["t"][5]), g["y"][5])        # dict surface of the reference (:472-480)
+    assert np.allclose(one["acceleration"], g["acceleration"][5], rtol=1e-12, atol=1e-17)
+    assert one["altitude"] == g["altitude"][5]
+
+
+# ------------------------------------------------------------------------- trajectories
+def test_c1_run_simulation_drop_in(Model, golden_dir):
+    """The reference's own call sequence (app.py:110,140,171,190) on C1."""
+    g = np.load(os.path.join(golden_dir, "c1_single.npz"))
+    m = Model(Cd=1.3, A=14.0, m=5000.0, epoch=float(g["epoch_jd"]), gmst0=0.0)
+    y0 = m.get_initial_state(7800, 0, 0, 120e3, 90, -1, gmst=0.0)
+    calls = []
+    sol = m.run_simulation((0, 800), y0, np.arange(0, 800, 1.0), progress_callback=lambda p, e: calls.append(p))
+    assert calls and calls[-1] == 1.0
+    assert sol.y.shape == (6, 695) and sol.t.shape == (695,) and sol.t[-1] == 694.0
+    assert sol.status == 1 and len(sol.t_events[0]) == 1
+    assert abs(sol.t_events[0][0] - float(g["o3_t_event"])) < T_ABS
+    assert abs(sol.t_events[0][0] - float(g["o2_t_event"])) < T_ABS
+    compare_states(sol.y.T, g["o3_ys"][:695], "C1 vs O3")
+    compare_states(sol.y.T, g["o2_y"].T, "C1 vs O2 (scipy pinned, unmodified RHS)")
+    assert np.allclose(sol.y_events[0][0], g["o3_y_event"], rtol=1e-9, atol=1e-6)
+    ad = sol.additional_data
+    assert ad["altitude"].shape == (695,) and ad["velocity"].shape == (695, 3) and ad["acceleration"].shape == (695, 3)
+    assert np.allclose(ad["altitude"], np.linalg.norm(sol.y[:3], axis=0) - 6378137.0, rtol=0, atol=1e-8)
+    assert np.array_equal(ad["velocity"], sol.y[3:6].T)
+    # loose agreement with the reference as shipped (adaptive): ~19 m
+    n1 = min(len(g["o1_t"]), 695)
+    assert np.max(np.linalg.norm(g["o1_y"].T[:n1, :3] - sol.y.T[:n1, :3], axis=1)) < 100.0
+    assert np.max(np.abs(g["o1_altitude"][:n1] - ad["altitude"][:n1])) < 100.0
+
+
+@pytest.mark.parametrize("name", ["c2_mc.npz", "edge.npz"])
+def test_golden_reentry(Model, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    res = run_golden(Model, g)
+    s = samples_np(res)
+    compare_states(s[:, :, :6], g["ys"], name)
+    assert np.array_equal(res.impact_step.cpu().numpy(), g["impact_step"].astype(np.int32))
+    hit = g["impact_step"] > 0
+    it = res.impact_time.cpu().numpy()
+    assert np.allclose(it[hit], g["t_event"][hit], rtol=0, atol=T_ABS) and np.all(np.isnan(it[~hit]))
+    fs = res.final_state.t().cpu().numpy()
+    assert np.allclose(fs[hit], g["y_event"][hit], rtol=1e-9, atol=1e-5)
+    st = res.status.cpu().numpy()
+    assert np.array_equal(st == 1, hit)
+    ns = res.n_samples.cpu().numpy()
+    assert np.array_equal(ns, (~np.isnan(g["ys"][:, :, 0])).sum(axis=1))
+    # altitude / speed columns
+    ok = ~np.isnan(s[:, :, 0])
+    assert np.allclose(s[ok][:, 6], np.linalg.norm(s[ok][:, :3], axis=1) - 6378137.0, rtol=0, atol=1e-8)
+    assert np.allclose(s[ok][:, 7], np.linalg.norm(s[ok][:, 3:6], axis=1), rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["c3_sso.npz", "c4_geo_heo.npz"])
+def test_golden_orbits(Model, golden_dir, name):
+    """Compared horizon: 1 day (C3) / 6 days (C4), strict."""
+    g = np.load(os.path.join(golden_dir, name))
+    res = run_golden(Model, g, steps_per_launch=1024)
+    compare_states(samples_np(res)[:, :, :6], g["ys"], name)
+    assert np.all(res.impact_step.cpu().numpy() == -1) and np.all(res.status.cpu().numpy() == 0)
+
+
+def test_mc_vs_oracle_512(Model, oracle):
+    """C2-shaped ensemble against the oracle on the same seeded inputs."""
+    from reentry_old_b200.configs import reentry_dispersion_params
+
+    n, n_steps, dt, stride = 512, 2048, 0.5, 16
+    p = reentry_dispersion_params(n, seed=4321)
+    m = Model(Cd=1.3, A=14.0, m=5000.0, epoch=2460310.5, gmst0=0.0)
+    y0 = m.get_initial_states(*p.T, gmst=0.0)
+    res = m.run_ensemble(y0, dt=dt, n_steps=n_steps, out_stride=stride)
+    ref = oracle.propagate(y0.cpu().numpy(), 1.3, 14.0, 5000.0, 2460310.5, 0.0, 0.0, dt, n_steps, stride)
+    compare_states(samples_np(res)[:, :, :6], ref["samples"][:, :, :6], "MC-512")
+    assert np.array_equal(res.impact_step.cpu().numpy(), ref["impact_step"])
+    assert np.allclose(res.impact_time.cpu().numpy(), ref["impact_time"], rtol=0, atol=T_ABS)
+    assert np.array_equal(res.n_samples.cpu().numpy(), ref["n_samples"].astype(np.int32))
+    assert np.array_equal(res.status.cpu().numpy(), ref["status"])
+    assert np.allclose(res.final_state.t().cpu().numpy(), ref["final_state"], rtol=1e-9, atol=1e-5)
+
+
+# -------------------------------------------------------------- launch-structure invariance
+def test_results_do_not_depend_on_launch_structure(Model, torch):
+    """Bit-identical results for any steps_per_launch / compaction / early-exit setting
+    (trajectories are independent; FSAL state and tiles carry no launch dependence)."""
+    from reentry_old_b200.configs import reentry_dispersion_params
+
+    n, n_steps = 3000, 1800
+    p = reentry_dispersion_params(n, seed=77)
+    p[:, 5] -= 0.5  # steeper: impacts spread over many launches
+    m = Model(Cd=1.3, A=14.0, m=5000.0)
+    y0 = m.get_initial_states(*p.T)
+    base = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=7)
+    for kw in (dict(steps_per_launch=16), dict(steps_per_launch=50), dict(steps_per_launch=n_steps),
+               dict(compact=False), dict(early_exit=False), dict(compact=False, early_exit=False, steps_per_launch=100)):
+        r = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=7, **kw)
+        for a, b in ((r.samples, base.samples), (r.final_state, base.final_state), (r.impact_time, base.impact_time)):
+            assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)), kw
+        assert torch.equal(r.impact_step, base.impact_step) and torch.equal(r.status, base.status), kw
+        assert torch.equal(r.n_samples, base.n_samples), kw
+
+
+def test_soa_input_and_per_trajectory_bodies(Model, torch, oracle):
+    rng = np.random.default_rng(8)
+    n = 300
+    from reentry_old_b200.configs import reentry_dispersion_params
+
+    p = reentry_dispersion_params(n, seed=5)
+    m = Model(Cd=9.9, A=9.9, m=9.9)  # scalars must be ignored when arrays are given
+    y0 = m.get_initial_states(*p.T)
+    Cd, A, mass = rng.uniform(1, 2.2, n), rng.uniform(1, 30, n), rng.uniform(200, 8000, n)
+    y0_soa_view = y0.t().contiguous().t()  # [N,6] view with strides (1, N)
+    assert y0_soa_view.stride() == (1, n)
+    r = m.run_ensemble(y0_soa_view, dt=0.5, n_steps=2600, out_stride=50, Cd=Cd, A=A, m=mass)
+    ref = oracle.propagate(y0.cpu().numpy(), Cd, A, mass, m.epoch, m.gmst0, 0.0, 0.5, 2600, 50)
+    compare_states(samples_np(r)[:, :, :6], ref["samples"][:, :, :6], "per-trajectory Cd/A/m")
+    assert np.array_equal(r.impact_step.cpu().numpy(), ref["impact_step"])
+
+
+# ----------------------------------------------------------------- size-independent properties
+def test_large_ensemble_properties(Model, torch, oracle):
+    """200k trajectories: properties that need no oracle run at full size + a strided oracle subsample."""
+    from reentry_old_b200.configs import reentry_dispersion_params
+
+    n, n_steps, stride = 200_000, 2048, 16
+    p = reentry_dispersion_params(n, seed=1234)
+    m = Model(Cd=1.3, A=14.0, m=5000.0)
+    y0 = m.get_initial_states(*p.T)
+    r = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=stride)
+    assert int((r.status == 1).sum()) == n
+    step = r.impact_step.to(torch.int64)
+    assert int(step.min()) > 900 and int(step.max()) < n_steps
+    t_imp = r.impact_time
+    assert bool(((t_imp > (step - 1) * 0.5) & (t_imp <= step * 0.5)).all())           # event inside its step
+    assert torch.equal(r.n_samples.to(torch.int64), (step - 1) // stride + 1)          # samples strictly before it
+    valid = ~torch.isnan(r.samples[:, 0, :])                                           # [n_out, N]
+    assert torch.equal(valid.sum(0).to(torch.int32), r.n_samples)                      # NaN exactly after the event
+    assert bool((valid[:-1] >= valid[1:]).all())                                       # validity is a prefix
+    alt_final = r.final_state[:3].norm(dim=0) - 6378137.0
+    assert float((alt_final - 1000.0).abs().max()) < 1e-6                              # dense-output root sits at 1000 m
+    alt = torch.where(valid, r.samples[:, 6, :], torch.full_like(r.samples[:, 6, :], 1e9))
+    assert float(alt.min()) > 1000.0                                                   # no stored sample below the event
+    sub = np.arange(0, n, n // 64)[:64]
+    ref = oracle.propagate(y0[sub].cpu().numpy(), 1.3, 14.0, 5000.0, m.epoch, m.gmst0, 0.0, 0.5, n_steps, stride)
+    compare_states(samples_np(r)[sub][:, :, :6], ref["samples"][:, :, :6], "200k subsample")
+    assert np.array_equal(r.impact_step[sub].cpu().numpy(), ref["impact_step"])
+    assert r.stats["propagate_launches"] < n_steps // 32  # early exit stopped the launch sequence
+
+
+# ----------------------------------------------------------------------- host-buffer (e2e) path
+def test_propagate_host_matches_device_path(Model, torch):
+    import ctypes as C
+
+    from reentry_old_b200 import _lib as L
+    from reentry_old_b200.configs import reentry_dispersion_params
+    from reentry_old_b200.model import DeviceContext
+
+    n, n_steps, stride = 5000, 2048, 16
+    p = reentry_dispersion_params(n, seed=11)
+    m = Model(Cd=1.3, A=14.0, m=5000.0)
+    y0 = m.get_initial_states(*p.T)
+    r = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=stride)
+    ctx = DeviceContext.get()
+    n_out = n_steps // stride + 1
+    y0h = y0.cpu().numpy()
+    samples = np.full((n_out, 8, n), np.nan)
+    fs = np.empty((n, 6)); istep = np.empty(n, np.int32); itime = np.empty(n); st = np.empty(n, np.uint8)
+    ns = np.empty(n, np.int32); used = C.c_int64(0)
+    run = L.RbRun(first_step=0, n_steps=n_steps, out_stride=stride, steps_per_launch=32, event_altitude=1000.0,
+                  flags=L.RB_FLAG_COMPACT)
+    rc = ctx.lib.rb_propagate_host(ctx.handle, n, y0h.ctypes.data, None, None, None, 1.3, 14.0, 5000.0, m.epoch, m.gmst0,
+                                   0.0, 0.5, C.byref(run), samples.ctypes.data, n_out, fs.ctypes.data, istep.ctypes.data,
+                                   itime.ctypes.data, st.ctypes.data, ns.ctypes.data, C.byref(used))
+    assert rc == 0, ctx.lib.rb_ctx_last_error(ctx.handle)
+    ctx.table_key = None  # the host call staged its own table
+    assert np.array_equal(istep, r.impact_step.cpu().numpy()) and np.array_equal(st, r.status.cpu().numpy())
+    assert np.array_equal(itime, r.impact_time.cpu().numpy()) and np.array_equal(ns, r.n_samples.cpu().numpy())
+    assert np.array_equal(fs, r.final_state.t().cpu().numpy())
+    k = used.value
+    assert ns.max() <= k <= n_out
+    assert np.array_equal(np.nan_to_num(samples[:k], nan=-1.0), np.nan_to_num(r.samples[:k].cpu().numpy(), nan=-1.0))
+
+
+def test_error_codes(Model, torch):
+    import ctypes as C
+
+    from reentry_old_b200 import _lib as L
+    from reentry_old_b200.model import DeviceContext
+
+    lib = L.load()
+    h = L.vp()
+    assert lib.rb_ctx_create(C.byref(h), 9999) == -1           # invalid device
+    assert lib.rb_ctx_create(C.byref(h), 0) == 0
+    rin, run, out = L.RbIn(n=4), L.RbRun(n_steps=10, out_stride=1), L.RbOut()
+    assert lib.rb_propagate(h, C.byref(rin), C.byref(run), C.byref(out), None) == -1   # null buffers
+    y0 = torch.zeros(4, 6, dtype=torch.float64, device="cuda")
+    fs = torch.zeros(6, 4, dtype=torch.float64, device="cuda")
+    st = torch.zeros(4, dtype=torch.uint8, device="cuda")
+    ist = torch.zeros(4, dtype=torch.int32, device="cuda")
+    rin = L.RbIn(n=4, y0=y0.data_ptr(), y0_traj_stride=6, y0_comp_stride=1, cd_scalar=1, area_scalar=1, mass_scalar=1)
+    out = L.RbOut(final_state=fs.data_ptr(), status=st.data_ptr(), impact_step=ist.data_ptr())
+    assert lib.rb_propagate(h, C.byref(rin), C.byref(run), C.byref(out), None) == -3   # no time table
+    tab = np.empty((lib.rb_time_table_entries(5), 16))
+    assert lib.rb_build_time_table(2460310.5, 0.0, 0.0, 1.0, 5, tab.ctypes.data, 1) == 0
+    assert lib.rb_ctx_set_time_table(h, tab.ctypes.data, 5, 0.0, 1.0, None) == 0
+    assert lib.rb_propagate(h, C.byref(rin), C.byref(run), C.byref(out), None) == -4   # 10 steps > table of 5
+    run.out_stride = 0
+    assert lib.rb_propagate(h, C.byref(rin), C.byref(run), C.byref(out), None) == -1
+    assert lib.rb_ctx_destroy(h) == 0
+    m = Model(sim_type="DOP853")
+    with pytest.raises(NotImplementedError):
+        m.run_ensemble(np.zeros((1, 6)), dt=1.0, n_steps=1)
+    with pytest.raises(ValueError):
+        Model().run_simulation((0, 10), np.ones(6), np.array([0.0, 1.0, 3.0]))          # non-uniform t_eval
+    # zero trajectories / zero steps are valid and empty
+    r = Model().run_ensemble(np.zeros((0, 6)), dt=1.0, n_steps=5)
+    assert r.samples.shape == (6, 8, 0)
+    y = Model().get_initial_state(7800, 0, 0, 120e3, 90, -1)
+    r = Model().run_ensemble(y[None], dt=1.0, n_steps=0)
+    assert r.samples.shape == (1, 8, 1) and int(r.status[0]) == 0 and np.allclose(r.samples[0, :6, 0].cpu().numpy(), y)
+
+
+def test_nonfinite_lane_is_retired(Model, torch):
+    m = Model()
+    y = m.get_initial_state(7800, 0, 0, 300e3, 90, 0)
+    y0 = np.stack([y, [0.0, 0.0, 0.0, 1.0, 0.0, 0.0], y])     # r = 0 -> division by zero -> NaN
+    r = m.run_ensemble(y0, dt=1.0, n_steps=64, out_stride=8)
+    assert r.status.cpu().tolist() == [0, 2, 0]
+    assert torch.equal(torch.nan_to_num(r.samples[:, :, 0]), torch.nan_to_num(r.samples[:, :, 2]))
+    assert int(r.impact_step[1]) == 1 and int(r.n_samples[1]) == 1
+
+
+def test_fp64_peak_probe(torch):
+    from reentry_old_b200.model import DeviceContext
+
+    tf = DeviceContext.get().fp64_peak_tflops(100.0)
+    assert 5.0 < tf < 80.0, tf

@@ -1,0 +1,172 @@
+"""CPU-side checks (no GPU): the C ABI loads and exports every declared symbol, the product's
+host time-table builder matches the oracle, and the product's __host__ __device__ physics
+source, compiled for the host (tests/host_harness.cu), matches the oracle and the golden RHS."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    from reentry_old_b200 import build as B
+    from reentry_old_b200 import _lib as L
+
+    B.build()
+    return L.load()
+
+
+@pytest.fixture(scope="session")
+def harness():
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "host_harness.so")
+    src = os.path.join(ROOT, "tests", "host_harness.cu")
+    deps = [src] + [os.path.join(ROOT, "reentry_old_b200", "csrc", f) for f in ("rb_kernels.cuh", "rb_physics.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
+                        "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "reentry_old_b200", "csrc"),
+                        "-o", so, src], check=True, env=env, capture_output=True)
+    h = C.CDLL(so)
+    d, vp = C.c_double, C.c_void_p
+    h.hh_time_entry.argtypes = [d, d, d, vp]
+    h.hh_acceleration.argtypes = [vp, vp, vp, d, d, d, vp, vp]
+    h.hh_geodetic_latitude_deg.restype = d
+    h.hh_geodetic_latitude_deg.argtypes = [d, d, d]
+    h.hh_density.restype = d
+    h.hh_density.argtypes = [d, d, d, vp]
+    h.hh_propagate.restype = C.c_int64
+    h.hh_propagate.argtypes = [vp, vp, d, d, d, d, C.c_int64, d, vp]
+    return h
+
+
+def test_abi_exports_every_declared_symbol(product_lib):
+    from reentry_old_b200 import _lib as L
+
+    hdr = open(os.path.join(ROOT, "include", "reentry_b200.h")).read()
+    declared = set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", hdr)) - {"rb_error", "rb_traj_status"}
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    for name in declared:
+        assert hasattr(product_lib, name), name
+    assert product_lib.rb_abi_version() == 1
+    assert product_lib.rb_strerror(0) == b"ok" and b"invalid" in product_lib.rb_strerror(-1)
+    assert product_lib.rb_time_table_entries(100) == 501
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from reentry_old_b200 import _lib as L
+
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.ReentryB200Error, match="no CPU fallback"):
+        L.load()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from reentry_old_b200 import ReentryB200Error, SpacecraftModel
+
+    with pytest.raises(ReentryB200Error):
+        SpacecraftModel().get_initial_state(7800, 0, 0, 120e3, 90, -1)
+
+
+@pytest.mark.parametrize("t0,dt,n_steps", [(0.0, 0.5, 200), (250.0, 1.0, 50), (0.0, 60.0, 3000), (10.0, 0.1, 40)])
+def test_time_table_builder_matches_oracle(product_lib, oracle, t0, dt, n_steps):
+    """rb_build_time_table (product host code) == the reference's own ephemeris/GMST/solar
+    functions evaluated at scipy's stage times (t_{n+1} = t_n + h; t_n + C_s h)."""
+    epoch, gmst0 = 2460310.5, 0.7
+    n_e = product_lib.rb_time_table_entries(n_steps)
+    tab = np.empty((n_e, 16))
+    assert product_lib.rb_build_time_table(epoch, gmst0, t0, dt, n_steps, tab.ctypes.data, 0) == 0
+    Cs = [0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1]
+    t = t0
+    times = [t0]
+    for n in range(n_steps):
+        times += [t + Cs[s] * dt for s in (1, 2, 3, 4)] + [t + dt]
+        t = t + dt
+    assert np.array_equal(tab[:, 15], np.array(times))
+    idx = np.unique(np.concatenate([np.arange(0, min(n_e, 30)), np.linspace(0, n_e - 1, 60).astype(int)]))
+    for e in idx:
+        ref = oracle.time_table_entry(tab[e, 15], epoch, gmst0)
+        assert np.array_equal(tab[e], ref), e
+    # single-thread and multi-thread builds are identical
+    tab1 = np.empty_like(tab)
+    assert product_lib.rb_build_time_table(epoch, gmst0, t0, dt, n_steps, tab1.ctypes.data, 1) == 0
+    assert np.array_equal(tab, tab1)
+
+
+def _entry(h, t, epoch, gmst0):
+    e = np.empty(16)
+    h.hh_time_entry(C.c_double(t), C.c_double(epoch), C.c_double(gmst0), e.ctypes.data)
+    return e
+
+
+def test_device_physics_source_vs_golden_rhs(harness, oracle, golden_dir):
+    """acceleration<>() of rb_physics.cuh (host build) vs the UNMODIFIED reference's
+    equations_of_motion on random states (golden) and vs the oracle, term by term."""
+    g = np.load(os.path.join(golden_dir, "rhs_random.npz"))
+    epoch, gmst0 = float(g["epoch_jd"]), float(g["gmst0"])
+    keys = ["acceleration", "gravitational_acceleration", "J2_acceleration", "moon_acceleration", "sun_acceleration",
+            "drag_acceleration"]
+    for i in range(len(g["t"])):
+        y = np.ascontiguousarray(g["y"][i])
+        e = _entry(harness, g["t"][i], epoch, gmst0)
+        a = np.empty(3); d = np.empty(22)
+        harness.hh_acceleration(e.ctypes.data, y[:3].ctypes.data, y[3:].copy().ctypes.data, C.c_double(float(g["Cd"])),
+                                C.c_double(float(g["A"])), C.c_double(float(g["m"])), a.ctypes.data, d.ctypes.data)
+        for k, key in enumerate(keys):
+            ref = g[key][i]
+            got = d[3 * k:3 * k + 3]
+            # third-body terms are differences of ~6e-3 m/s^2 terms: allow 1 ulp of those (2e-18)
+            assert np.all(np.abs(got - ref) <= 4e-15 * np.linalg.norm(ref) + 2e-18), (key, i, got, ref)
+        assert d[18] == g["altitude"][i]
+        _, parts = oracle.equations_of_motion(g["t"][i], y, epoch, gmst0, float(g["Cd"]), float(g["A"]), float(g["m"]))
+        assert abs(d[19] - parts["latitude_deg"]) <= 1e-12 * max(1.0, abs(parts["latitude_deg"]))
+        assert abs(d[20] - parts["rho"]) <= 1e-14 * parts["rho"]
+
+
+def test_geodetic_iteration_quirk(harness, oracle):
+    """The stale-iterate break rule of coordinate_converter.py:87-93 is reproduced."""
+    rng = np.random.default_rng(5)
+    for _ in range(500):
+        r = rng.normal(size=3); r *= rng.uniform(6.38e6, 8e6) / np.linalg.norm(r)
+        ref = oracle.ecef_to_geodetic(*r)[0]
+        got = harness.hh_geodetic_latitude_deg(C.c_double(r[0]), C.c_double(r[1]), C.c_double(r[2]))
+        assert abs(got - ref) <= 1e-13 * max(1.0, abs(ref))
+    assert abs(harness.hh_geodetic_latitude_deg(C.c_double(1260744.91), C.c_double(-4705164.05), C.c_double(4840901.80))
+               - 45.0000007295818) < 1e-12
+
+
+@pytest.mark.parametrize("name,idx", [("c1_single.npz", 0), ("c2_mc.npz", 3), ("edge.npz", 2), ("c3_sso.npz", 1)])
+def test_device_stage_arithmetic_vs_golden(harness, product_lib, golden_dir, name, idx):
+    """The kernel's stage arithmetic (fma chains + table entries), run on the host, against the
+    golden trajectories of the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, name))
+    y0 = np.ascontiguousarray(g["y0"].reshape(-1, 6)[idx])
+    pick = lambda k: float(np.atleast_1d(g[k]).ravel()[idx if np.size(g[k]) > 1 else 0])
+    n_steps = int(g["n_steps"]); dt = float(g["dt"]); t0 = float(g["t0"])
+    stride = int(g["stride"]) if "stride" in g else 1
+    n_e = product_lib.rb_time_table_entries(n_steps)
+    tab = np.empty((n_e, 16))
+    assert product_lib.rb_build_time_table(float(g["epoch_jd"]), float(g["gmst0"]), t0, dt, n_steps, tab.ctypes.data, 0) == 0
+    ys = np.full((n_steps + 1, 6), np.nan)
+    imp = harness.hh_propagate(tab.ctypes.data, y0.ctypes.data, C.c_double(pick("Cd")), C.c_double(pick("A")),
+                               C.c_double(pick("m")), C.c_double(dt), C.c_int64(n_steps), C.c_double(1000.0), ys.ctypes.data)
+    ref = g["o3_ys"] if name == "c1_single.npz" else g["ys"][idx]
+    ref_imp = int(g["o3_impact_step"]) if name == "c1_single.npz" else int(g["impact_step"][idx])
+    assert imp == ref_imp
+    got = ys[::stride]
+    ok = ~np.isnan(ref[:, 0])
+    assert np.array_equal(ok, ~np.isnan(got[:, 0]))
+    rel = np.linalg.norm(got[ok, :3] - ref[ok, :3], axis=1) / np.linalg.norm(ref[ok, :3], axis=1)
+    relv = np.linalg.norm(got[ok, 3:] - ref[ok, 3:], axis=1) / np.linalg.norm(ref[ok, 3:], axis=1)
+    assert rel.max() < 1e-11 and relv.max() < 1e-11
