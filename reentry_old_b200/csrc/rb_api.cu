@@ -295,7 +295,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             CK(cudaEventSynchronize(ctx->poll_ev[slot]));
             const int32_t seen = ctx->h_poll[slot];
             ctx->stats.last_polled_live = seen;
-            live_bound = std::min<int64_t>(live_bound, seen);
+            if (compact) live_bound = std::min<int64_t>(live_bound, seen);  // the list only shrinks when compacted
             if (seen == 0) break;
         }
         const int64_t steps = std::min<int64_t>(spl, run->n_steps - done);

@@ -171,8 +171,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     int32_t tid = 0;
     double y[6] = {0, 0, 0, 0, 0, 0};
     Body body{p.cd_s, p.area_s, p.mass_s};
+    bool loaded = false;
     if (alive) {
         tid = p.live[i];
+        alive = p.status[tid] == RB_TRAJ_ALIVE;  // without compaction the list still names retired lanes
+    }
+    if (alive) {
+        loaded = true;
 #pragma unroll
         for (int c = 0; c < 6; ++c) y[c] = p.state[c * p.n + tid];
         if (p.cd) body.cd = p.cd[tid];
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         }
     }
 done:
-    if (i < n_live) {
+    if (loaded) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) p.state[c * p.n + tid] = y[c];
     }
