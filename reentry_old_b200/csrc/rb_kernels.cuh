@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     // per-trajectory state
     int32_t tid = 0;
     double y[6] = {0, 0, 0, 0, 0, 0};
-    Body body{p.cd_s, p.area_s, p.mass_s};
+    double b_cd = p.cd_s, b_area = p.area_s, b_mass = p.mass_s;
     bool loaded = false;
     if (alive) {
         tid = p.live[i];
@@ -180,10 +180,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         loaded = true;
 #pragma unroll
         for (int c = 0; c < 6; ++c) y[c] = p.state[c * p.n + tid];
-        if (p.cd) body.cd = p.cd[tid];
-        if (p.area) body.area = p.area[tid];
-        if (p.mass) body.mass = p.mass[tid];
+        if (p.cd) b_cd = p.cd[tid];
+        if (p.area) b_area = p.area[tid];
+        if (p.mass) b_mass = p.mass[tid];
     }
+    const Body body = make_body(b_cd, b_area, b_mass);
     double g_old = event_g(y, p.event_altitude);
     __syncthreads();  // barrier init visible to all before anyone waits
 
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
     if (st == RB_TRAJ_IMPACTED && p.refine && p.impact_step && p.impact_time) {
         const int64_t n_abs = (int64_t)p.impact_step[tid] - 1;
         const double *e0 = p.table + (RB_STAGES_PER_STEP * n_abs) * ENTRY_DOUBLES;
-        Body body{p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s};
+        const Body body = make_body(p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s);
         double y[6], K[7][6], ys[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) y[c] = p.state[c * p.n + tid];
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(128) k_eom(int64_t n, const double *t, const d
     time_entry(t[i], epoch_jd, gmst0, e);
     double r[3] = {y[0 * n + i], y[1 * n + i], y[2 * n + i]};
     double v[3] = {y[3 * n + i], y[4 * n + i], y[5 * n + i]};
-    Body body{cd ? cd[i] : cd_s, area ? area[i] : area_s, mass ? mass[i] : mass_s};
+    const Body body = make_body(cd ? cd[i] : cd_s, area ? area[i] : area_s, mass ? mass[i] : mass_s);
     double a[3];
     RhsOut d;
     acceleration<true>(e, r, v, body, a, &d);

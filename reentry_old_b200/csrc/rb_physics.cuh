@@ -15,12 +15,7 @@
 #include <stdint.h>
 
 #include "reentry_constants.h"
-
-#if defined(__CUDACC__)
-#define RB_HD __host__ __device__ __forceinline__
-#else
-#define RB_HD inline
-#endif
+#include "rb_math.cuh"
 
 namespace rb {
 
@@ -30,9 +25,10 @@ enum : int {
     ENTRY_DOUBLES = 16
 };
 
-struct Body {  // per-trajectory constants (SpacecraftModel.Cd / .A / .m, spacecraft_model.py:394-397)
-    double cd, area, mass;
+struct Body {  // per-trajectory constant bc = 0.5 Cd A / m (SpacecraftModel.Cd / .A / .m, spacecraft_model.py:394-397, :204-206)
+    double bc;
 };
+RB_HD Body make_body(double cd, double area, double mass) { return Body{0.5 * cd * area / mass}; }
 
 struct RhsOut {  // optional diagnostics (dict of spacecraft_model.py:472-480)
     double a_grav[3], a_j2[3], a_moon[3], a_sun[3], a_drag[3];
@@ -62,120 +58,139 @@ RB_HD Layer layer_of(double altitude, int &idx) {
     return l;
 }
 
-// Geodetic latitude in DEGREES of an ECEF point: coordinate_converter.py:81-96 with its quirks
+// |geodetic latitude| in DEGREES of an ECEF point: coordinate_converter.py:81-96 with its quirks
 // (theta built with (1 - e2*R); the loop tests |lat - lat_new| < 1e-6 BEFORE lat = lat_new, so
-// the previous iterate is returned; at most 100 iterations).
-RB_HD double geodetic_latitude_deg(double x, double y, double z) {
+// the PREVIOUS iterate is returned; at most 100 iterations).
+//
+// B200 form: every angle of the reference's iteration is carried as its (sin, cos) pair.
+// atan2(a, b) followed by sin/cos is the normalisation (a, b)/hypot(a, b), and
+// |lat - lat_new| < tol is |sin(lat - lat_new)| = |s c' - c s'| < sin(tol) -- the same iterates
+// and the same break decision as the reference, with ONE inverse-trig call (the returned
+// angle itself) instead of 2 + n atan2 and 1 + n sincos.  Only |lat| is needed by the density
+// (spacecraft_model.py:76).  Uses N + h = p / cos(lat) (coordinate_converter.py:89).
+//   p2 = x^2 + y^2, inv_p = 1/sqrt(p2) are passed in (shared with the caller).
+RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
     const double e2R = RB_EARTH_E2 * RB_EARTH_R;
-    const double p = sqrt(x * x + y * y);
-    const double theta = atan2(z * RB_EARTH_R, p * (1.0 - e2R));
-    double st, ct;
-    sincos(theta, &st, &ct);
-    double lat = atan2(z + e2R * (st * (st * st)), p - e2R * (ct * (ct * ct)));
-    const double zp = z / p;
+    const double p = p2 * inv_p;
+    // theta = atan2(z R, p (1 - e2 R))
+    const double ta = z * RB_EARTH_R, tb = p * (1.0 - e2R);
+    const double th = rb_rsqrt(ta * ta + tb * tb);
+    const double st = ta * th, ct = tb * th;
+    // lat = atan2(z + e2R sin^3 theta, p - e2R cos^3 theta)
+    const double la = z + e2R * (st * (st * st)), lb = p - e2R * (ct * (ct * ct));
+    const double lh = rb_rsqrt(la * la + lb * lb);
+    double s = la * lh, c = lb * lh;
+    const double zp = z * inv_p;
+    const double sin_tol = 9.999999999998333e-07;  // sin(1e-6)
     for (int k = 0; k < RB_GEODETIC_MAX_ITER; ++k) {
-        double sl, cl;
-        sincos(lat, &sl, &cl);
-        const double N = RB_EARTH_R / sqrt(1.0 - RB_EARTH_E2 * (sl * sl));
-        const double h = p / cl - N;
-        const double lat_new = atan2(zp, 1.0 - RB_EARTH_E2 * N / (N + h));
-        if (fabs(lat - lat_new) < RB_GEODETIC_TOL) break;
-        lat = lat_new;
+        const double N = RB_EARTH_R * rb_rsqrt(1.0 - RB_EARTH_E2 * (s * s));
+        const double b = 1.0 - RB_EARTH_E2 * N * c * inv_p;   // 1 - e2 N / (N + h)
+        const double nh = rb_rsqrt(zp * zp + b * b);
+        const double s2 = zp * nh, c2 = b * nh;               // lat_new = atan2(z/p, b)
+        if (fabs(s * c2 - c * s2) < sin_tol) break;          // |lat - lat_new| < 1e-6
+        s = s2; c = c2;
     }
-    return lat * (180.0 / RB_PI);
+    return atan2(fabs(s), c) * (180.0 / RB_PI);
 }
 
 // Density (and temperature) -- atmosphere_model / simplified_nrlmsise_00 / solar_activity_factor
 // (spacecraft_model.py:181-188, :71-99, :148-168, :110-127).  solar_time = time-only part of the
-// solar factor from the time table.
-RB_HD double density(double altitude, double latitude_deg, double solar_time, double &T_out) {
+// solar factor from the time table.  The two exponentials of the top layer (:84 and :89) are
+// one exp of the summed exponent.
+RB_HD double density(double altitude, double abs_latitude_deg, double solar_time, double &T_out) {
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
     if (altitude < RB_SOLAR_BLEND_ALT) {
         const double ks = RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS;
-        const double normalized = 1.0 / (1.0 + exp(-ks * (altitude - RB_SIGMOID_X0)));
-        factor = 1.0 + (factor - 1.0) * normalized;
+        const double normalized = rb_rcp(1.0 + exp(-ks * (altitude - RB_SIGMOID_X0)));
+        factor = fma(factor - 1.0, normalized, 1.0);
     }
-    const double latitude_factor = 1.0 + RB_LAT_FACTOR_COEF * fabs(latitude_deg) / 90.0;
-    int i;
-    const Layer l = layer_of(altitude, i);
-    const double dh = altitude - l.h;
-    const double T = l.T + l.L * dh;
+    const double latitude_factor = fma(RB_LAT_FACTOR_COEF / 90.0, abs_latitude_deg, 1.0);
     const double gM = -RB_EARTH_GRAVITY * RB_AIR_MOLAR_MASS;
-    double P;
-    if (l.L == 0.0) P = l.P * exp(gM * dh / (RB_GAS_CONSTANT * l.T));
-    else P = l.P * pow(T / l.T, gM / (RB_GAS_CONSTANT * l.L));
-    if (i == RB_N_LAYERS - 1) P *= exp(-(altitude - l.h) / RB_SCALE_HEIGHT);
-    P *= latitude_factor;
-    double rho = P / (RB_R_GAS * T);
-    rho *= factor;
+    double P, T;
+    if (altitude >= 84852.0) {  // top layer (i == 7): isothermal + the extra scale-height tail
+        const double dh = altitude - 84852.0;
+        const double bt7[RB_N_LAYERS] = RB_BASE_TEMPERATURES_INIT;
+        const double bp7[RB_N_LAYERS] = RB_BASE_PRESSURES_INIT;
+        T = bt7[7];
+        P = bp7[7] * exp(dh * (gM / (RB_GAS_CONSTANT * bt7[7]) - 1.0 / RB_SCALE_HEIGHT));
+    } else {
+        int i;
+        const Layer l = layer_of(altitude, i);
+        const double dh = altitude - l.h;
+        T = fma(l.L, dh, l.T);
+        if (l.L == 0.0) P = l.P * exp(dh * (gM / (RB_GAS_CONSTANT * l.T)));
+        else P = l.P * pow(T / l.T, gM / (RB_GAS_CONSTANT * l.L));
+    }
     T_out = T;
-    return rho;
+    return P * latitude_factor * rb_rcp(RB_R_GAS * T) * factor;
 }
 
 // Full acceleration of SpacecraftModel.equations_of_motion (spacecraft_model.py:437-470).
-// e: time-table entry (16 doubles).  Returns |r| through r_norm_out.
+// e: time-table entry (16 doubles).  b.mass is used through b.bc = 0.5 Cd A / m.
 template <bool DIAG>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
                         double a[3], RhsOut *diag) {
     const double x = r[0], y = r[1], z = r[2];
-    const double r2 = x * x + y * y + z * z;
-    const double rn = sqrt(r2);                       // euclidean_norm, :67-69, :439
+    const double p2 = fma(x, x, y * y);
+    const double r2 = fma(z, z, p2);
+    const double ir = rb_rsqrt(r2);                   // 1/|r|
+    const double rn = r2 * ir;                        // |r|  (euclidean_norm, :67-69, :439)
+    const double ir2 = ir * ir, ir3 = ir2 * ir;
     const double cg = e[E_CG], sg = e[E_SG];          // cos/sin(gmst0 + EARTH_OMEGA t), :443
-    // ECI -> ECEF (coordinate_converter.py:29-48) for position and velocity, :446-447
-    const double xe = cg * x + sg * y, ye = cg * y - sg * x, ze = z;
-    const double vgx = cg * v[0] + sg * v[1], vgy = cg * v[1] - sg * v[0], vgz = v[2];
-    // v_rel = v_ground - omega x r_ecef, :448
-    const double vrx = vgx + RB_EARTH_OMEGA * ye, vry = vgy - RB_EARTH_OMEGA * xe, vrz = vgz;
+    // ground velocity (coordinate_converter.py:29-48, :447) and v_rel = v_ground - omega x r_ecef (:448);
+    // rotating omega x r_ecef back is omega x r_eci, so v_rel is formed in ECI and |v_rel| is frame free
+    const double wx = v[0] + RB_EARTH_OMEGA * y, wy = v[1] - RB_EARTH_OMEGA * x, wz = v[2];
     // point-mass gravity, :451 : -mu r / |r|^3
-    const double rn2 = rn * rn;
-    const double inv_r3 = 1.0 / (rn * rn2);
-    const double gk = -RB_EARTH_MU * inv_r3;
+    const double gk = -RB_EARTH_MU * ir3;
     double ax = gk * x, ay = gk * y, az = gk * z;
     if (DIAG) { diag->a_grav[0] = ax; diag->a_grav[1] = ay; diag->a_grav[2] = az; }
     // J2, :377-388 : f = 1.5 mu J2 R^2 / r^5 ; a = f r (5 z^2/r^2 - {1,1,3})
     {
-        const double inv_r2 = 1.0 / rn2;
-        const double f = (1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R)) * (inv_r3 * inv_r2);
-        const double q = 5.0 * (z * z) * inv_r2;
-        const double jx = (q - 1.0) * x * f, jy = (q - 1.0) * y * f, jz = (q - 3.0) * z * f;
+        const double f = (1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R)) * (ir3 * ir2);
+        const double q = 5.0 * (z * z) * ir2;
+        const double fxy = (q - 1.0) * f, fz = (q - 3.0) * f;
+        const double jx = fxy * x, jy = fxy * y, jz = fz * z;
         ax += jx; ay += jy; az += jz;
         if (DIAG) { diag->a_j2[0] = jx; diag->a_j2[1] = jy; diag->a_j2[2] = jz; }
     }
     // third bodies, :355-363 : k d/|d|^3 - k s/|s|^3 (the second term is time-only -> table)
     {
         const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
-        const double dn = sqrt(dx * dx + dy * dy + dz * dz);
-        const double k3 = RB_MOON_K / (dn * (dn * dn));
-        const double mx = k3 * dx - e[E_MOON_IND + 0], my = k3 * dy - e[E_MOON_IND + 1], mz = k3 * dz - e[E_MOON_IND + 2];
+        const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+        const double k3 = RB_MOON_K * (id * id * id);
+        const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
         ax += mx; ay += my; az += mz;
         if (DIAG) { diag->a_moon[0] = mx; diag->a_moon[1] = my; diag->a_moon[2] = mz; }
     }
     {
         const double dx = e[E_SUN + 0] - x, dy = e[E_SUN + 1] - y, dz = e[E_SUN + 2] - z;
-        const double dn = sqrt(dx * dx + dy * dy + dz * dz);
-        const double k3 = RB_SUN_K / (dn * (dn * dn));
-        const double sx = k3 * dx - e[E_SUN_IND + 0], sy = k3 * dy - e[E_SUN_IND + 1], sz = k3 * dz - e[E_SUN_IND + 2];
+        const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+        const double k3 = RB_SUN_K * (id * id * id);
+        const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
         ax += sx; ay += sy; az += sz;
         if (DIAG) { diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz; }
     }
-    // drag, :458-465 : spherical altitude, geodetic latitude (deg), density, -1/2 rho Cd A |v| v / m, back to ECI
+    // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
+    // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
     {
         const double altitude = rn - RB_EARTH_R;
-        const double lat_deg = geodetic_latitude_deg(xe, ye, ze);
+        // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
+        const double ip = rb_rsqrt(p2);
+        const double lat_deg = geodetic_abs_latitude_deg(p2, ip, z);
         double T;
         const double rho = density(altitude, lat_deg, e[E_SOLAR], T);
-        const double vn = sqrt(vrx * vrx + vry * vry + vrz * vrz);
-        const double Fd = 0.5 * rho * b.cd * b.area * (vn * vn);      // :204
-        const double kd = -(Fd / vn) / b.mass;                          // :205-206
-        const double dxe = kd * vrx, dye = kd * vry, dze = kd * vrz;
-        const double ddx = cg * dxe - sg * dye, ddy = sg * dxe + cg * dye;  // ecef_to_eci, cc:50-68
-        ax += ddx; ay += ddy; az += dze;
+        const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
+        const double vn = w2 * rb_rsqrt(w2);
+        const double kd = -(rho * b.bc) * vn;
+        const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;
+        ax += ddx; ay += ddy; az += ddz;
         if (DIAG) {
-            diag->a_drag[0] = ddx; diag->a_drag[1] = ddy; diag->a_drag[2] = dze;
+            diag->a_drag[0] = ddx; diag->a_drag[1] = ddy; diag->a_drag[2] = ddz;
             diag->altitude = altitude; diag->latitude_deg = lat_deg; diag->rho = rho; diag->T = T;
         }
     }
+    (void)cg; (void)sg;
     a[0] = ax; a[1] = ay; a[2] = az;
 }
 

@@ -17,7 +17,7 @@ void hh_time_entry(double t, double epoch0, double gmst0, double *e) { time_entr
 
 void hh_acceleration(const double *e, const double *r, const double *v, double cd, double area, double mass, double *a,
                      double *diag22) {
-    Body b{cd, area, mass};
+    const Body b = make_body(cd, area, mass);
     RhsOut d;
     acceleration<true>(e, r, v, b, a, &d);
     if (diag22) {
@@ -29,14 +29,17 @@ void hh_acceleration(const double *e, const double *r, const double *v, double c
     }
 }
 
-double hh_geodetic_latitude_deg(double x, double y, double z) { return geodetic_latitude_deg(x, y, z); }
+double hh_geodetic_latitude_deg(double x, double y, double z) {
+    const double p2 = x * x + y * y;
+    return geodetic_abs_latitude_deg(p2, rb_rsqrt(p2), z);
+}
 double hh_density(double alt, double lat, double solar_time, double *T) { return density(alt, lat, solar_time, *T); }
 
 // Same stage arithmetic as k_propagate (fma chains, table entries), on the host, one trajectory.
 // table: [(5*n_steps+1)][16].  ys_out: [n_steps+1][6].  Returns the impact step or -1.
 int64_t hh_propagate(const double *table, const double *y0, double cd, double area, double mass, double h,
                      int64_t n_steps, double event_altitude, double *ys_out) {
-    Body b{cd, area, mass};
+    const Body b = make_body(cd, area, mass);
     double y[6], K[7][6], ys[6];
     memcpy(y, y0, sizeof y);
     memcpy(ys_out, y, sizeof y);
