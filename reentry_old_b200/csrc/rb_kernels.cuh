@@ -26,10 +26,49 @@ namespace rb {
 constexpr int TILE_STEPS = 16;                                      // steps per time-table tile
 constexpr int TILE_ENTRIES = RB_STAGES_PER_STEP * TILE_STEPS + 1;  // 81 entries
 constexpr int TILE_DOUBLES = TILE_ENTRIES * ENTRY_DOUBLES;          // 1296 doubles = 10368 B
-constexpr int K_SLOTS = 7;                                          // K0..K6
+constexpr int K_SLOTS = 7;                                          // Ka_0..Ka_6 (acceleration rows only)
+constexpr int K_ROWS = 3;
 
-__constant__ double c_A[7][6] = {RB_DP_A_ROWS};
+__constant__ Tableau c_T = make_tableau();  // run-time operands from the constant bank
 __constant__ double c_P[7][4] = {RB_DP_P_ROWS};
+
+// Stage state of stage S (1..6; 6 = the step's end point, row 6 of A = B):
+//   v_s = v_n + h sum_j a_sj Ka_j ;  r_s = r_n + (c_s h) v_n + h^2 sum_j abar_sj Ka_j
+// Ka_j lives in shared memory at Kt[(slot_j*3 + c)*BLOCK]; slot_0 = k0 (FSAL toggle), slot_j = j.
+template <int S, int BLOCK>
+__device__ __forceinline__ void stage_state(const double *Kt, int k0, const double y[6], double h, double hh,
+                                            double ys[6]) {
+    double dv[3], dr[3];
+    {
+        const double *K0 = Kt + (k0 * K_ROWS) * BLOCK;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double k = K0[c * BLOCK];
+            dv[c] = c_T.a[S][0] * k;
+            dr[c] = (S >= 2) ? c_T.abar[S][0] * k : 0.0;
+        }
+    }
+#pragma unroll
+    for (int j = 1; j < S; ++j) {
+        const bool use_v = !(S == 6 && j == 1);  // B[1] = 0
+        const bool use_r = (j <= S - 2);          // abar[s][s-1] = 0
+        if (!use_v && !use_r) continue;
+        const double *Kj = Kt + (j * K_ROWS) * BLOCK;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double k = Kj[c * BLOCK];
+            if (use_v) dv[c] = fma(c_T.a[S][j], k, dv[c]);
+            if (use_r) dr[c] = fma(c_T.abar[S][j], k, dr[c]);
+        }
+    }
+    const double ch = c_T.c[S] * h;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        ys[3 + c] = fma(dv[c], h, y[3 + c]);
+        const double base = fma(ch, y[3 + c], y[c]);
+        ys[c] = (S >= 2) ? fma(dr[c], hh, base) : base;
+    }
+}
 
 struct StepParams {
     // time table
@@ -130,10 +169,10 @@ __global__ void k_init(const InitParams p) {
 }
 
 // ---------------------------------------------------------------- the hot kernel
-// Shared memory: [2 x tile][K slots: 7 x 6 x BLOCK doubles][2 mbarriers]
+// Shared memory: [2 x tile][Ka slots: 7 x 3 x BLOCK doubles][2 mbarriers]
 template <int BLOCK>
 constexpr size_t propagate_smem_bytes() {
-    return sizeof(double) * (2 * TILE_DOUBLES + K_SLOTS * 6 * BLOCK) + 2 * sizeof(uint64_t);
+    return sizeof(double) * (2 * TILE_DOUBLES + K_SLOTS * K_ROWS * BLOCK) + 2 * sizeof(uint64_t);
 }
 
 template <int BLOCK, int MIN_BLOCKS>
@@ -141,7 +180,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
     double *Ks = tiles + 2 * TILE_DOUBLES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Ks + K_SLOTS * 6 * BLOCK);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Ks + K_SLOTS * K_ROWS * BLOCK);
 
     const int n_live = *p.n_live;
     const int64_t i0 = (int64_t)blockIdx.x * BLOCK;
@@ -188,55 +227,46 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     double g_old = event_g(y, p.event_altitude);
     __syncthreads();  // barrier init visible to all before anyone waits
 
-    double *Kt = Ks + threadIdx.x;  // slot s, component c at Kt[(s*6 + c)*BLOCK]
-    int k0 = 0;                     // slot currently holding K0 (toggles 0 <-> 6, FSAL without a copy)
+    double *Kt = Ks + threadIdx.x;  // Ka of slot s, component c at Kt[(s*3 + c)*BLOCK]
+    int k0 = 0;                     // slot currently holding Ka_0 (toggles 0 <-> 6, FSAL without a copy)
     int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));  // steps until the next stored sample
     int64_t next_k = p.run_step0 / p.out_stride + 1;
-    const double h = p.h;
+    const double h = p.h, hh = p.h * p.h;
 
     for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
         const double *tile = tiles + (t & 1) * TILE_DOUBLES;
         const int ts = tile_steps_of(t);
         // stage loop flattened so that the acceleration code exists ONCE in the kernel:
-        // s = 0 only for the very first evaluation of the launch (K0 = f(t_n, y_n)).
+        // s = 0 only for the very first evaluation of the launch (Ka_0 = a(t_n, y_n)).
         int m = 0;
         int s = (t == 0) ? 0 : 1;
         while (m < ts) {
             if (alive) {
                 double ys[6];
-                const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
-                if (s == 0) {
+                switch (s) {
+                    case 0:
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) ys[c] = y[c];
-                } else {
-                    // dy = sum_j A[s][j] K_j ; ys = y + dy*h   (scipy rk.py:62-66; row 6 = B)
-                    double acc[6];
-                    {
-                        const double a0 = c_A[s][0];
-                        const double *K0p = Kt + (k0 * 6) * BLOCK;
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) acc[c] = a0 * K0p[c * BLOCK];
-                    }
-                    for (int j = 1; j < s; ++j) {
-                        const double aj = c_A[s][j];
-                        const double *Kj = Kt + (j * 6) * BLOCK;
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) acc[c] = fma(aj, Kj[c * BLOCK], acc[c]);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) ys[c] = fma(acc[c], h, y[c]);
+                        for (int c = 0; c < 6; ++c) ys[c] = y[c];
+                        break;
+                    case 1: stage_state<1, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    case 2: stage_state<2, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    case 3: stage_state<3, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    case 4: stage_state<4, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    case 5: stage_state<5, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    default: stage_state<6, BLOCK>(Kt, k0, y, h, hh, ys); break;
                 }
+                const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
                 double a[3];
                 acceleration<false>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
-                double *Ksl = Kt + (slot_s * 6) * BLOCK;
-                Ksl[0 * BLOCK] = ys[3]; Ksl[1 * BLOCK] = ys[4]; Ksl[2 * BLOCK] = ys[5];
-                Ksl[3 * BLOCK] = a[0];  Ksl[4 * BLOCK] = a[1];  Ksl[5 * BLOCK] = a[2];
+                double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
+                Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
                 if (s == 6) {
                     // step complete: ys = y_{n+1}
-                    const double rn_new = sqrt(ys[0] * ys[0] + ys[1] * ys[1] + ys[2] * ys[2]);
-                    const double g_new = rn_new - RB_EARTH_R - p.event_altitude;
+                    const double r2n = fma(ys[2], ys[2], fma(ys[0], ys[0], ys[1] * ys[1]));
+                    const double rn_new = r2n * rb_rsqrt(r2n);
+                    const double g_new = rn_new - KC(earth_r) - p.event_altitude;
                     const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
                     const bool finite = fabs(ys[0] + ys[1] + ys[2] + ys[3] + ys[4] + ys[5]) <= DBL_MAX;
                     if (!finite) {
@@ -255,8 +285,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                             double *sp = p.samples + next_k * p.sample_stride + tid;
 #pragma unroll
                             for (int c = 0; c < 6; ++c) st_stream(sp + c * p.field_stride, ys[c]);
-                            st_stream(sp + 6 * p.field_stride, rn_new - RB_EARTH_R);
-                            st_stream(sp + 7 * p.field_stride, sqrt(ys[3] * ys[3] + ys[4] * ys[4] + ys[5] * ys[5]));
+                            st_stream(sp + 6 * p.field_stride, rn_new - KC(earth_r));
+                            const double v2 = fma(ys[5], ys[5], fma(ys[3], ys[3], ys[4] * ys[4]));
+                            st_stream(sp + 7 * p.field_stride, sqrt(v2));
                         }
                     }
                 }
@@ -459,13 +490,17 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
         double y[6], K[7][6], ys[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) y[c] = p.state[c * p.n + tid];
-        const double h = p.h;
+        const double h = p.h, hh = p.h * p.h;
 #pragma unroll 1
         for (int s = 0; s <= 6; ++s) {
-            for (int c = 0; c < 6; ++c) {
-                double acc = 0.0;
-                for (int j = 0; j < s; ++j) acc = (j == 0) ? c_A[s][0] * K[0][c] : fma(c_A[s][j], K[j][c], acc);
-                ys[c] = (s == 0) ? y[c] : fma(acc, h, y[c]);
+            for (int c = 0; c < 3; ++c) {
+                double dv = 0.0, dr = 0.0;
+                for (int j = 0; j < s; ++j) {
+                    dv = (j == 0) ? c_T.a[s][0] * K[0][3 + c] : fma(c_T.a[s][j], K[j][3 + c], dv);
+                    dr = (j == 0) ? c_T.abar[s][0] * K[0][3 + c] : fma(c_T.abar[s][j], K[j][3 + c], dr);
+                }
+                ys[3 + c] = (s == 0) ? y[3 + c] : fma(dv, h, y[3 + c]);
+                ys[c] = (s == 0) ? y[c] : fma(dr, hh, fma(c_T.c[s] * h, y[3 + c], y[c]));
             }
             double a[3];
             acceleration<false>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);

@@ -25,6 +25,50 @@ enum : int {
     ENTRY_DOUBLES = 16
 };
 
+// ---- constants of the hot RHS, kept in the constant bank ---------------------------------
+// A 64-bit literal that is not a 32-bit-encodable immediate costs two UMOVs per use on sm_100
+// (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
+// for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
+struct Consts {
+    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, e2, e2r, one_m_e2r, sin_tol, rad2deg, latc;
+    double sig_ks, sig_x0, blend_alt, inv_rgas_dummy, rgas, top_h, top_T, top_P, top_k;
+    double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
+    double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
+    double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
+    double inv_bt[RB_N_LAYERS];  // 1 / T_i
+};
+
+#define RB_GM_ (-RB_EARTH_GRAVITY * RB_AIR_MOLAR_MASS)
+#define RB_T_(i) (rb_bt_(i))
+constexpr double rb_bp_(int i) { constexpr double a[RB_N_LAYERS] = RB_ALTITUDE_BREAKPOINTS_INIT; return a[i]; }
+constexpr double rb_gr_(int i) { constexpr double a[RB_N_LAYERS] = RB_TEMPERATURE_GRADIENTS_INIT; return a[i]; }
+constexpr double rb_bt_(int i) { constexpr double a[RB_N_LAYERS] = RB_BASE_TEMPERATURES_INIT; return a[i]; }
+constexpr double rb_bpz_(int i) { constexpr double a[RB_N_LAYERS] = RB_BASE_PRESSURES_INIT; return a[i]; }
+constexpr double rb_isok_(int i) { return RB_GM_ / (RB_GAS_CONSTANT * rb_bt_(i)); }
+constexpr double rb_powk_(int i) { return rb_gr_(i) == 0.0 ? 0.0 : RB_GM_ / (RB_GAS_CONSTANT * rb_gr_(i)); }
+#define RB_L8_(f) {f(0), f(1), f(2), f(3), f(4), f(5), f(6), f(7)}
+constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
+
+#define RB_CONSTS_INIT                                                                              \
+    {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
+     RB_MOON_K, RB_SUN_K, RB_EARTH_R, RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
+     1.0 - RB_EARTH_E2 * RB_EARTH_R, 9.999999999998333e-07 /* sin(1e-6) */, 180.0 / RB_PI,           \
+     RB_LAT_FACTOR_COEF / 90.0, RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
+     RB_SOLAR_BLEND_ALT, 0.0, RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
+     rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
+     RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
+     RB_L8_(rb_powk_), RB_L8_(rb_invbt_)}
+
+#if defined(__CUDACC__)
+__constant__ Consts c_k = RB_CONSTS_INIT;
+#endif
+static const Consts h_k = RB_CONSTS_INIT;
+#if defined(__CUDA_ARCH__)
+#define KC(f) (rb::c_k.f)
+#else
+#define KC(f) (rb::h_k.f)
+#endif
+
 struct Body {  // per-trajectory constant bc = 0.5 Cd A / m (SpacecraftModel.Cd / .A / .m, spacecraft_model.py:394-397, :204-206)
     double bc;
 };
@@ -34,29 +78,6 @@ struct RhsOut {  // optional diagnostics (dict of spacecraft_model.py:472-480)
     double a_grav[3], a_j2[3], a_moon[3], a_sun[3], a_drag[3];
     double altitude, latitude_deg, rho, T;
 };
-
-// USSA-1976-style layer table (constants.py:124-127) and derived per-layer exponents.
-// Kept as scalar switch so the values become immediates / constant-bank operands.
-struct Layer { double h, L, T, P; };
-
-RB_HD Layer layer_of(double altitude, int &idx) {
-    // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1   (spacecraft_model.py:79)
-    const double bp[RB_N_LAYERS] = RB_ALTITUDE_BREAKPOINTS_INIT;
-    const double gr[RB_N_LAYERS] = RB_TEMPERATURE_GRADIENTS_INIT;
-    const double bt[RB_N_LAYERS] = RB_BASE_TEMPERATURES_INIT;
-    const double bpz[RB_N_LAYERS] = RB_BASE_PRESSURES_INIT;
-    int i = 0;
-#pragma unroll
-    for (int k = 1; k < RB_N_LAYERS; ++k) i += (altitude >= bp[k]) ? 1 : 0;
-    idx = i;
-    Layer l;
-    // select by compare chain (no local-memory indexing)
-    l.h = bp[0]; l.L = gr[0]; l.T = bt[0]; l.P = bpz[0];
-#pragma unroll
-    for (int k = 1; k < RB_N_LAYERS; ++k)
-        if (i == k) { l.h = bp[k]; l.L = gr[k]; l.T = bt[k]; l.P = bpz[k]; }
-    return l;
-}
 
 // |geodetic latitude| in DEGREES of an ECEF point: coordinate_converter.py:81-96 with its quirks
 // (theta built with (1 - e2*R); the loop tests |lat - lat_new| < 1e-6 BEFORE lat = lat_new, so
@@ -70,27 +91,27 @@ RB_HD Layer layer_of(double altitude, int &idx) {
 // (spacecraft_model.py:76).  Uses N + h = p / cos(lat) (coordinate_converter.py:89).
 //   p2 = x^2 + y^2, inv_p = 1/sqrt(p2) are passed in (shared with the caller).
 RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
-    const double e2R = RB_EARTH_E2 * RB_EARTH_R;
     const double p = p2 * inv_p;
     // theta = atan2(z R, p (1 - e2 R))
-    const double ta = z * RB_EARTH_R, tb = p * (1.0 - e2R);
-    const double th = rb_rsqrt(ta * ta + tb * tb);
+    const double ta = z * KC(earth_r), tb = p * KC(one_m_e2r);
+    const double th = rb_rsqrt(fma(ta, ta, tb * tb));
     const double st = ta * th, ct = tb * th;
     // lat = atan2(z + e2R sin^3 theta, p - e2R cos^3 theta)
-    const double la = z + e2R * (st * (st * st)), lb = p - e2R * (ct * (ct * ct));
-    const double lh = rb_rsqrt(la * la + lb * lb);
+    const double la = fma(KC(e2r), st * (st * st), z), lb = fma(-KC(e2r), ct * (ct * ct), p);
+    const double lh = rb_rsqrt(fma(la, la, lb * lb));
     double s = la * lh, c = lb * lh;
     const double zp = z * inv_p;
-    const double sin_tol = 9.999999999998333e-07;  // sin(1e-6)
-    for (int k = 0; k < RB_GEODETIC_MAX_ITER; ++k) {
-        const double N = RB_EARTH_R * rb_rsqrt(1.0 - RB_EARTH_E2 * (s * s));
-        const double b = 1.0 - RB_EARTH_E2 * N * c * inv_p;   // 1 - e2 N / (N + h)
-        const double nh = rb_rsqrt(zp * zp + b * b);
-        const double s2 = zp * nh, c2 = b * nh;               // lat_new = atan2(z/p, b)
-        if (fabs(s * c2 - c * s2) < sin_tol) break;          // |lat - lat_new| < 1e-6
+    const double zp2 = zp * zp;
+    const double k = KC(e2r) * inv_p;                              // e2 R / p
+    for (int it = 0; it < RB_GEODETIC_MAX_ITER; ++it) {
+        const double w = rb_rsqrt(fma(-KC(e2), s * s, 1.0));       // N = R w
+        const double b = fma(-k * w, c, 1.0);                      // 1 - e2 N / (N + h),  N + h = p / cos(lat)
+        const double nh = rb_rsqrt(fma(b, b, zp2));
+        const double s2 = zp * nh, c2 = b * nh;                    // lat_new = atan2(z/p, b)
+        if (fabs(fma(s, c2, -(c * s2))) < KC(sin_tol)) break;     // |lat - lat_new| < 1e-6
         s = s2; c = c2;
     }
-    return atan2(fabs(s), c) * (180.0 / RB_PI);
+    return atan2(fabs(s), c) * KC(rad2deg);
 }
 
 // Density (and temperature) -- atmosphere_model / simplified_nrlmsise_00 / solar_activity_factor
@@ -100,30 +121,28 @@ RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
 RB_HD double density(double altitude, double abs_latitude_deg, double solar_time, double &T_out) {
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
-    if (altitude < RB_SOLAR_BLEND_ALT) {
-        const double ks = RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS;
-        const double normalized = rb_rcp(1.0 + exp(-ks * (altitude - RB_SIGMOID_X0)));
+    if (altitude < KC(blend_alt)) {
+        const double normalized = rb_rcp(1.0 + exp(-KC(sig_ks) * (altitude - KC(sig_x0))));
         factor = fma(factor - 1.0, normalized, 1.0);
     }
-    const double latitude_factor = fma(RB_LAT_FACTOR_COEF / 90.0, abs_latitude_deg, 1.0);
-    const double gM = -RB_EARTH_GRAVITY * RB_AIR_MOLAR_MASS;
+    const double latitude_factor = fma(KC(latc), abs_latitude_deg, 1.0);
     double P, T;
-    if (altitude >= 84852.0) {  // top layer (i == 7): isothermal + the extra scale-height tail
-        const double dh = altitude - 84852.0;
-        const double bt7[RB_N_LAYERS] = RB_BASE_TEMPERATURES_INIT;
-        const double bp7[RB_N_LAYERS] = RB_BASE_PRESSURES_INIT;
-        T = bt7[7];
-        P = bp7[7] * exp(dh * (gM / (RB_GAS_CONSTANT * bt7[7]) - 1.0 / RB_SCALE_HEIGHT));
+    if (altitude >= KC(top_h)) {  // top layer (i == 7): isothermal + the extra scale-height tail
+        T = KC(top_T);
+        P = KC(top_P) * exp((altitude - KC(top_h)) * KC(top_k));
     } else {
-        int i;
-        const Layer l = layer_of(altitude, i);
-        const double dh = altitude - l.h;
-        T = fma(l.L, dh, l.T);
-        if (l.L == 0.0) P = l.P * exp(dh * (gM / (RB_GAS_CONSTANT * l.T)));
-        else P = l.P * pow(T / l.T, gM / (RB_GAS_CONSTANT * l.L));
+        // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
+        int i = (altitude >= KC(bp[4])) ? 4 : 0;
+        i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
+        i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
+        const double dh = altitude - KC(bp[i]);
+        const double L = KC(gr[i]);
+        T = fma(L, dh, KC(bt[i]));
+        if (L == 0.0) P = KC(bpz[i]) * exp(dh * KC(iso_k[i]));
+        else P = KC(bpz[i]) * pow(T * KC(inv_bt[i]), KC(pow_k[i]));
     }
     T_out = T;
-    return P * latitude_factor * rb_rcp(RB_R_GAS * T) * factor;
+    return P * latitude_factor * rb_rcp(KC(rgas) * T) * factor;
 }
 
 // Full acceleration of SpacecraftModel.equations_of_motion (spacecraft_model.py:437-470).
@@ -137,17 +156,16 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     const double ir = rb_rsqrt(r2);                   // 1/|r|
     const double rn = r2 * ir;                        // |r|  (euclidean_norm, :67-69, :439)
     const double ir2 = ir * ir, ir3 = ir2 * ir;
-    const double cg = e[E_CG], sg = e[E_SG];          // cos/sin(gmst0 + EARTH_OMEGA t), :443
     // ground velocity (coordinate_converter.py:29-48, :447) and v_rel = v_ground - omega x r_ecef (:448);
     // rotating omega x r_ecef back is omega x r_eci, so v_rel is formed in ECI and |v_rel| is frame free
-    const double wx = v[0] + RB_EARTH_OMEGA * y, wy = v[1] - RB_EARTH_OMEGA * x, wz = v[2];
+    const double wx = fma(KC(omega), y, v[0]), wy = fma(-KC(omega), x, v[1]), wz = v[2];
     // point-mass gravity, :451 : -mu r / |r|^3
-    const double gk = -RB_EARTH_MU * ir3;
+    const double gk = KC(neg_mu) * ir3;
     double ax = gk * x, ay = gk * y, az = gk * z;
     if (DIAG) { diag->a_grav[0] = ax; diag->a_grav[1] = ay; diag->a_grav[2] = az; }
     // J2, :377-388 : f = 1.5 mu J2 R^2 / r^5 ; a = f r (5 z^2/r^2 - {1,1,3})
     {
-        const double f = (1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R)) * (ir3 * ir2);
+        const double f = KC(j2f) * (ir3 * ir2);
         const double q = 5.0 * (z * z) * ir2;
         const double fxy = (q - 1.0) * f, fz = (q - 3.0) * f;
         const double jx = fxy * x, jy = fxy * y, jz = fz * z;
@@ -158,7 +176,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     {
         const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
         const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-        const double k3 = RB_MOON_K * (id * id * id);
+        const double k3 = KC(moon_k) * (id * id * id);
         const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
         ax += mx; ay += my; az += mz;
         if (DIAG) { diag->a_moon[0] = mx; diag->a_moon[1] = my; diag->a_moon[2] = mz; }
@@ -166,7 +184,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     {
         const double dx = e[E_SUN + 0] - x, dy = e[E_SUN + 1] - y, dz = e[E_SUN + 2] - z;
         const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-        const double k3 = RB_SUN_K * (id * id * id);
+        const double k3 = KC(sun_k) * (id * id * id);
         const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
         ax += sx; ay += sy; az += sz;
         if (DIAG) { diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz; }
@@ -174,7 +192,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
     // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
     {
-        const double altitude = rn - RB_EARTH_R;
+        const double altitude = rn - KC(earth_r);
         // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
         const double ip = rb_rsqrt(p2);
         const double lat_deg = geodetic_abs_latitude_deg(p2, ip, z);
@@ -190,13 +208,13 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
             diag->altitude = altitude; diag->latitude_deg = lat_deg; diag->rho = rho; diag->T = T;
         }
     }
-    (void)cg; (void)sg;
     a[0] = ax; a[1] = ay; a[2] = az;
 }
 
 // event function of run_simulation.altitude_event (spacecraft_model.py:496-501)
 RB_HD double event_g(const double r[3], double event_altitude) {
-    return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) - RB_EARTH_R - event_altitude;
+    const double r2 = fma(r[2], r[2], fma(r[0], r[0], r[1] * r[1]));
+    return r2 * rb_rsqrt(r2) - KC(earth_r) - event_altitude;
 }
 
 // ---- Dormand-Prince tableau (scipy rk.py:541-565), row 6 of A = B (FSAL) ----
@@ -217,5 +235,35 @@ RB_HD double event_g(const double r[3], double event_altitude) {
     {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},          \
     {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},                       \
     {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}
+
+// The ODE is second order (y' = [v, a(t, r, v)]), so the position rows of every stage vector K_j
+// are the stage velocities v_j = v_n + h sum_i a_ji Ka_i.  Substituting them (Nystrom form),
+//   v_s = v_n + h   sum_{j<s} a_sj  Ka_j
+//   r_s = r_n + h c_s v_n + h^2 sum_{j<s-1} abar_sj Ka_j,   abar_sj = sum_{j<i<s} a_si a_ij,
+// is the same Runge-Kutta step (identical in exact arithmetic, rounding-level different from
+// scipy's K-matrix form) and only the three acceleration rows of each K_j have to be kept.
+struct Tableau {
+    double a[7][6];     // a_sj
+    double abar[7][6];  // abar_sj
+    double c[7];        // c_s = sum_j a_sj
+};
+constexpr Tableau make_tableau() {
+    Tableau t{};
+    constexpr double A[7][6] = {RB_DP_A_ROWS};
+    for (int s = 0; s < 7; ++s) {
+        double cs = 0.0;
+        for (int j = 0; j < 6; ++j) { t.a[s][j] = A[s][j]; cs += A[s][j]; t.abar[s][j] = 0.0; }
+        t.c[s] = cs;
+    }
+    for (int s = 0; s < 7; ++s)
+        for (int j = 0; j < s; ++j) {
+            double v = 0.0;
+            for (int i = j + 1; i < s && i < 6; ++i) v += A[s][i] * A[i][j];
+            t.abar[s][j] = v;
+        }
+    // exact stage abscissae of the tableau (the sums above are within 1 ulp of these)
+    t.c[0] = 0.0; t.c[1] = 1.0 / 5; t.c[2] = 3.0 / 10; t.c[3] = 4.0 / 5; t.c[4] = 8.0 / 9; t.c[5] = 1.0; t.c[6] = 1.0;
+    return t;
+}
 
 }  // namespace rb

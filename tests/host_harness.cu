@@ -9,7 +9,6 @@
 
 using namespace rb;
 
-static const double A_[7][6] = {RB_DP_A_ROWS};
 
 extern "C" {
 
@@ -35,32 +34,37 @@ double hh_geodetic_latitude_deg(double x, double y, double z) {
 }
 double hh_density(double alt, double lat, double solar_time, double *T) { return density(alt, lat, solar_time, *T); }
 
-// Same stage arithmetic as k_propagate (fma chains, table entries), on the host, one trajectory.
-// table: [(5*n_steps+1)][16].  ys_out: [n_steps+1][6].  Returns the impact step or -1.
+// Same stage arithmetic as k_propagate (Nystrom form, fma chains, table entries), on the host,
+// one trajectory.  table: [(5*n_steps+1)][16].  ys_out: [n_steps+1][6].  Returns the impact step or -1.
 int64_t hh_propagate(const double *table, const double *y0, double cd, double area, double mass, double h,
                      int64_t n_steps, double event_altitude, double *ys_out) {
+    static const Tableau T = make_tableau();
     const Body b = make_body(cd, area, mass);
-    double y[6], K[7][6], ys[6];
+    double y[6], Ka[7][3], ys[6];
     memcpy(y, y0, sizeof y);
     memcpy(ys_out, y, sizeof y);
     double g_old = event_g(y, event_altitude);
+    const double hh = h * h;
     int k0 = 0;
     for (int64_t n = 0; n < n_steps; ++n) {
         for (int s = (n == 0 ? 0 : 1); s <= 6; ++s) {
             const int slot = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
             if (s == 0) memcpy(ys, y, sizeof y);
             else {
-                double acc[6];
-                for (int c = 0; c < 6; ++c) acc[c] = A_[s][0] * K[k0][c];
-                for (int j = 1; j < s; ++j)
-                    for (int c = 0; c < 6; ++c) acc[c] = fma(A_[s][j], K[j][c], acc[c]);
-                for (int c = 0; c < 6; ++c) ys[c] = fma(acc[c], h, y[c]);
+                for (int c = 0; c < 3; ++c) {
+                    double dv = T.a[s][0] * Ka[k0][c];
+                    double dr = (s >= 2) ? T.abar[s][0] * Ka[k0][c] : 0.0;
+                    for (int j = 1; j < s; ++j) {
+                        if (T.a[s][j] != 0.0) dv = fma(T.a[s][j], Ka[j][c], dv);
+                        if (T.abar[s][j] != 0.0) dr = fma(T.abar[s][j], Ka[j][c], dr);
+                    }
+                    ys[3 + c] = fma(dv, h, y[3 + c]);
+                    const double base = fma(T.c[s] * h, y[3 + c], y[c]);
+                    ys[c] = (s >= 2) ? fma(dr, hh, base) : base;
+                }
             }
             const int64_t e = 5 * n + ((s == 6) ? 5 : s);
-            double a[3];
-            acceleration<false>(table + e * 16, ys, ys + 3, b, a, nullptr);
-            K[slot][0] = ys[3]; K[slot][1] = ys[4]; K[slot][2] = ys[5];
-            K[slot][3] = a[0]; K[slot][4] = a[1]; K[slot][5] = a[2];
+            acceleration<false>(table + e * 16, ys, ys + 3, b, Ka[slot], nullptr);
         }
         const double g_new = event_g(ys, event_altitude);
         if (g_old >= 0.0 && g_new <= 0.0) return n + 1;
