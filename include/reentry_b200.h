@@ -173,6 +173,12 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
 void *rb_host_alloc(int64_t bytes); /* pinned host memory (cudaHostAlloc) or NULL */
 void rb_host_free(void *p);
 
+/* Self-test hook for the library's own FP64 primitives (csrc/rb_math.cuh), elementwise on device
+ * arrays: op 0 rcp(x), 1 rsqrt(x), 2 exp(x), 3 log(x) for x in [0.7, 1.3], 4 atan2(x, y) for
+ * x, y >= 0 on the unit circle, 5 pow(x, y) for x in [0.7, 1.3].  y may be NULL for unary ops. */
+int32_t rb_math_probe(rb_ctx *ctx, int32_t op, int64_t n, const double *x, const double *y, double *out,
+                      void *stream);
+
 /* FP64 FMA peak probe used for the roofline denominator (MEASURED_PEAKS.json has no FP64
  * figure): runs a register-resident DFMA kernel for about `ms` milliseconds on `stream`,
  * returns achieved TFLOP/s (DFMA = 2 flop). */

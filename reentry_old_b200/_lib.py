@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libreentry_b200.so")
+LIB_PATH = os.environ.get("RB_LIB_PATH") or os.path.join(PKG, "libreentry_b200.so")  # RB_LIB_PATH: kernel-variant sweeps
 
 RB_FLAG_COMPACT = 1
 RB_FLAG_EARLY_EXIT = 2
@@ -65,6 +65,7 @@ SIGNATURES = {
                                 vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]),
     "rb_host_alloc": (vp, [i64]),
     "rb_host_free": (None, [vp]),
+    "rb_math_probe": (i32, [vp, i32, i64, vp, vp, vp, vp]),
     "rb_fp64_peak_probe": (i32, [vp, f64, C.POINTER(f64), vp]),
 }
 

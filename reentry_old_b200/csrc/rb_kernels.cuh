@@ -23,9 +23,12 @@
 
 namespace rb {
 
-constexpr int TILE_STEPS = 16;                                      // steps per time-table tile
-constexpr int TILE_ENTRIES = RB_STAGES_PER_STEP * TILE_STEPS + 1;  // 81 entries
-constexpr int TILE_DOUBLES = TILE_ENTRIES * ENTRY_DOUBLES;          // 1296 doubles = 10368 B
+#ifndef RB_TILE_STEPS
+#define RB_TILE_STEPS 8
+#endif
+constexpr int TILE_STEPS = RB_TILE_STEPS;                                      // steps per time-table tile
+constexpr int TILE_ENTRIES = RB_STAGES_PER_STEP * TILE_STEPS + 1;  // 41 entries
+constexpr int TILE_DOUBLES = TILE_ENTRIES * ENTRY_DOUBLES;          // 656 doubles = 5248 B
 constexpr int K_SLOTS = 7;                                          // Ka_0..Ka_6 (acceleration rows only)
 constexpr int K_ROWS = 3;
 
@@ -642,6 +645,24 @@ __global__ void __launch_bounds__(128) k_eom(int64_t n, const double *t, const d
     o[19 * n] = d.latitude_deg;
     o[20 * n] = d.rho;
     o[21 * n] = d.T;
+}
+
+// ---------------------------------------------------------------- self-test of rb_math.cuh
+__global__ void k_math_probe(int op, int64_t n, const double *x, const double *y, double *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = x[i], b = y ? y[i] : 0.0;
+    double r;
+    switch (op) {
+        case 0: r = rb_rcp(a); break;
+        case 1: r = rb_rsqrt(a); break;
+        case 2: r = rb_exp(a); break;
+        case 3: r = rb_log_near1(a); break;
+        case 4: r = rb_atan2_unit(a, b); break;
+        case 5: r = rb_pow_near1(a, b); break;
+        default: r = nan("");
+    }
+    out[i] = r;
 }
 
 // ---------------------------------------------------------------- FP64 FMA peak probe

@@ -30,7 +30,7 @@ enum : int {
 // (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
-    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, e2, e2r, one_m_e2r, sin_tol, rad2deg, latc;
+    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r, tan_tol, rad2deg, latc;
     double sig_ks, sig_x0, blend_alt, inv_rgas_dummy, rgas, top_h, top_T, top_P, top_k;
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
@@ -51,8 +51,8 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
 
 #define RB_CONSTS_INIT                                                                              \
     {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
-     RB_MOON_K, RB_SUN_K, RB_EARTH_R, RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
-     1.0 - RB_EARTH_E2 * RB_EARTH_R, 9.999999999998333e-07 /* sin(1e-6) */, 180.0 / RB_PI,           \
+     RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
+     1.0 - RB_EARTH_E2 * RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 180.0 / RB_PI,           \
      RB_LAT_FACTOR_COEF / 90.0, RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
      RB_SOLAR_BLEND_ALT, 0.0, RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
@@ -83,35 +83,43 @@ struct RhsOut {  // optional diagnostics (dict of spacecraft_model.py:472-480)
 // (theta built with (1 - e2*R); the loop tests |lat - lat_new| < 1e-6 BEFORE lat = lat_new, so
 // the PREVIOUS iterate is returned; at most 100 iterations).
 //
-// B200 form: every angle of the reference's iteration is carried as its (sin, cos) pair.
-// atan2(a, b) followed by sin/cos is the normalisation (a, b)/hypot(a, b), and
-// |lat - lat_new| < tol is |sin(lat - lat_new)| = |s c' - c s'| < sin(tol) -- the same iterates
-// and the same break decision as the reference, with ONE inverse-trig call (the returned
-// angle itself) instead of 2 + n atan2 and 1 + n sincos.  Only |lat| is needed by the density
-// (spacecraft_model.py:76).  Uses N + h = p / cos(lat) (coordinate_converter.py:89).
+// B200 form: every angle of the reference's iteration is carried as an (A, B) pair with
+// tan(angle) = A / B, B > 0 -- atan2(a, b) followed by sin/cos is a normalisation that cancels:
+//   N cos(lat) = R B / sqrt(B^2 + (1 - e2) A^2)                       (N = R / sqrt(1 - e2 sin^2 lat))
+//   lat_new    = atan2(z/p, 1 - e2 N / (N + h)),  N + h = p / cos(lat) (coordinate_converter.py:89-90)
+//              = pair (z/p, 1 - (e2 R / p) B / sqrt(B^2 + (1 - e2) A^2))
+//   |lat - lat_new| < tol  <=>  |A B' - A' B| < tan(tol) (B B' + A A')
+// i.e. the same iterates and the same break decision as the reference with ONE rsqrt per
+// iteration and ONE inverse-trig call (the returned angle) instead of 2 + n atan2 and 1 + n
+// sincos.  Only |lat| is needed by the density (spacecraft_model.py:76).
 //   p2 = x^2 + y^2, inv_p = 1/sqrt(p2) are passed in (shared with the caller).
 RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
     const double p = p2 * inv_p;
-    // theta = atan2(z R, p (1 - e2 R))
+    // theta = atan2(z R, p (1 - e2 R)) -> (sin, cos) by normalisation
     const double ta = z * KC(earth_r), tb = p * KC(one_m_e2r);
     const double th = rb_rsqrt(fma(ta, ta, tb * tb));
     const double st = ta * th, ct = tb * th;
-    // lat = atan2(z + e2R sin^3 theta, p - e2R cos^3 theta)
-    const double la = fma(KC(e2r), st * (st * st), z), lb = fma(-KC(e2r), ct * (ct * ct), p);
-    const double lh = rb_rsqrt(fma(la, la, lb * lb));
-    double s = la * lh, c = lb * lh;
-    const double zp = z * inv_p;
-    const double zp2 = zp * zp;
-    const double k = KC(e2r) * inv_p;                              // e2 R / p
-    for (int it = 0; it < RB_GEODETIC_MAX_ITER; ++it) {
-        const double w = rb_rsqrt(fma(-KC(e2), s * s, 1.0));       // N = R w
-        const double b = fma(-k * w, c, 1.0);                      // 1 - e2 N / (N + h),  N + h = p / cos(lat)
-        const double nh = rb_rsqrt(fma(b, b, zp2));
-        const double s2 = zp * nh, c2 = b * nh;                    // lat_new = atan2(z/p, b)
-        if (fabs(fma(s, c2, -(c * s2))) < KC(sin_tol)) break;     // |lat - lat_new| < 1e-6
-        s = s2; c = c2;
+    // lat_0 = atan2(z + e2R sin^3 theta, p - e2R cos^3 theta)
+    double A = fma(KC(e2r), st * (st * st), z), B = fma(-KC(e2r), ct * (ct * ct), p);
+    const double zp = z * inv_p;          // A of every later iterate
+    const double ke = KC(e2r) * inv_p;    // e2 R / p
+    {
+        const double q = rb_rsqrt(fma(B, B, KC(one_m_e2) * (A * A)));
+        const double Bn = fma(-ke * B, q, 1.0);
+        const bool conv = fabs(fma(A, Bn, -(zp * B))) < KC(tan_tol) * fma(B, Bn, A * zp);
+        if (!conv) {
+            A = zp; B = Bn;
+            const double zp2 = zp * zp, g = KC(one_m_e2) * zp2, azp = fabs(zp);
+            for (int it = 1; it < RB_GEODETIC_MAX_ITER; ++it) {
+                const double q2 = rb_rsqrt(fma(B, B, g));
+                const double Bn2 = fma(-ke * B, q2, 1.0);
+                if (azp * fabs(Bn2 - B) < KC(tan_tol) * fma(B, Bn2, zp2)) break;
+                B = Bn2;
+            }
+        }
     }
-    return atan2(fabs(s), c) * KC(rad2deg);
+    const double nr = rb_rsqrt(fma(A, A, B * B));
+    return rb_atan2_unit(fabs(A) * nr, B * nr) * KC(rad2deg);
 }
 
 // Density (and temperature) -- atmosphere_model / simplified_nrlmsise_00 / solar_activity_factor
@@ -122,14 +130,14 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
     if (altitude < KC(blend_alt)) {
-        const double normalized = rb_rcp(1.0 + exp(-KC(sig_ks) * (altitude - KC(sig_x0))));
+        const double normalized = rb_rcp(1.0 + rb_exp(-KC(sig_ks) * (altitude - KC(sig_x0))));
         factor = fma(factor - 1.0, normalized, 1.0);
     }
     const double latitude_factor = fma(KC(latc), abs_latitude_deg, 1.0);
     double P, T;
     if (altitude >= KC(top_h)) {  // top layer (i == 7): isothermal + the extra scale-height tail
         T = KC(top_T);
-        P = KC(top_P) * exp((altitude - KC(top_h)) * KC(top_k));
+        P = KC(top_P) * rb_exp((altitude - KC(top_h)) * KC(top_k));
     } else {
         // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
         int i = (altitude >= KC(bp[4])) ? 4 : 0;
@@ -138,8 +146,8 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
         const double dh = altitude - KC(bp[i]);
         const double L = KC(gr[i]);
         T = fma(L, dh, KC(bt[i]));
-        if (L == 0.0) P = KC(bpz[i]) * exp(dh * KC(iso_k[i]));
-        else P = KC(bpz[i]) * pow(T * KC(inv_bt[i]), KC(pow_k[i]));
+        if (L == 0.0) P = KC(bpz[i]) * rb_exp(dh * KC(iso_k[i]));
+        else P = KC(bpz[i]) * rb_pow_near1(T * KC(inv_bt[i]), KC(pow_k[i]));
     }
     T_out = T;
     return P * latitude_factor * rb_rcp(KC(rgas) * T) * factor;

@@ -322,6 +322,47 @@ def test_nonfinite_lane_is_retired(Model, torch):
     assert int(r.impact_step[1]) == 1 and int(r.n_samples[1]) == 1
 
 
+def test_math_primitives(torch):
+    """The guard-free FP64 primitives of csrc/rb_math.cuh against numpy (float64, correctly rounded libm)."""
+    from reentry_old_b200 import _lib as L
+    from reentry_old_b200.model import DeviceContext
+
+    ctx = DeviceContext.get()
+    rng = np.random.default_rng(0)
+    n = 200_000
+
+    def run(op, x, y=None):
+        xd = torch.as_tensor(x, device="cuda")
+        yd = torch.as_tensor(y, device="cuda") if y is not None else None
+        out = torch.empty_like(xd)
+        ctx.check(ctx.lib.rb_math_probe(ctx.handle, op, n, xd.data_ptr(), yd.data_ptr() if yd is not None else None,
+                                        out.data_ptr(), None))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    def ulps(got, ref):
+        return np.max(np.abs(got - ref) / np.spacing(np.abs(ref)))
+
+    x = 10 ** rng.uniform(-30, 30, n)
+    assert ulps(run(0, x), 1.0 / x) <= 1.0
+    assert ulps(run(1, x), 1.0 / np.sqrt(x)) <= 2.0   # vs a twice-rounded reference
+    x = np.concatenate([rng.uniform(-700, 5, n - 4), [0.0, -1e-300, -707.9, 1.0]])
+    assert ulps(run(2, x), np.exp(x)) <= 1.5
+    assert run(2, np.full(n, -1e5)).max() < 1e-300 and np.isnan(run(2, np.full(n, np.nan))).all()
+    x = rng.uniform(0.7, 1.3, n)
+    assert np.max(np.abs(run(3, x) - np.log(x))) <= 1.2e-16
+    # pow as the density uses it: (T/T_i)^(-gM/(R* L_i)) inside each gradient layer (constants.py:124-127)
+    layer = rng.integers(0, 5, n)
+    lo = np.array([0.7518, 1.0, 1.0, 0.7930, 0.8709])[layer]; hi = np.array([1.0, 1.0554, 1.1837, 1.0, 1.0])[layer]
+    k = np.array([5.2558, -34.163, -12.201, 12.201, 17.081])[layer]
+    x = rng.uniform(lo, hi)
+    assert np.max(np.abs(run(5, x, k) / np.power(x, k) - 1.0)) <= 2e-15
+    th = np.concatenate([rng.uniform(0, np.pi / 2, n - 5), [0.0, np.pi / 2, np.pi / 4, 1e-9, np.pi / 2 - 1e-9]])
+    s, c = np.sin(th), np.cos(th)
+    nrm = np.hypot(s, c); s, c = s / nrm, c / nrm
+    assert np.max(np.abs(run(4, s, c) - np.arctan2(s, c))) <= 4.5e-16
+
+
 def test_fp64_peak_probe(torch):
     from reentry_old_b200.model import DeviceContext
 
