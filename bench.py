@@ -30,7 +30,17 @@ METRIC = "fp64_trajectory_steps_per_s"
 UNIT = "traj-steps/s"
 # Algorithmic FP64 work per trajectory-step (DESIGN.md "Roofline"): SURVEY.md 8(d) cap of 6.5 kflop
 # (HW-weighted, DFMA = 2) lowered to the ncu-measured executed flop of the kernel when that is smaller.
-FLOP_PER_TRAJ_STEP = float(os.environ.get("RB_FLOP_PER_TRAJ_STEP", "6500"))
+def _flop_per_traj_step():
+    if "RB_FLOP_PER_TRAJ_STEP" in os.environ:
+        return float(os.environ["RB_FLOP_PER_TRAJ_STEP"]), "env"
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "flop_per_traj_step.json")))
+        return min(float(d["flop_per_traj_step"]), float(d.get("cap_survey_8d", 6500.0))), d.get("source", "profiles")
+    except Exception:
+        return 6500.0, "SURVEY.md 8(d) cap (no ncu calibration found)"
+
+
+FLOP_PER_TRAJ_STEP, FLOP_SOURCE = _flop_per_traj_step()
 SAMPLE_BYTES = 64
 SUMMARY_BYTES = 8 * 6 + 4 + 8 + 1 + 4
 
@@ -177,6 +187,8 @@ def main():
         raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     W = max(args.warmup, 3)
     K = args.steps
@@ -249,7 +261,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "k_propagate", "kernel_ms_per_pass": kern_ms, "kernel_launches_per_pass": n_prop,
-                "kernel_share_of_step": kern_ms / (ms / K), "flop_per_traj_step": FLOP_PER_TRAJ_STEP,
+                "kernel_share_of_step": kern_ms / (ms / K), "flop_per_traj_step": FLOP_PER_TRAJ_STEP, "flop_source": FLOP_SOURCE,
                 "peak_source": "DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure); "
                                "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
                 "output_write": {"bytes_per_pass": sample_bytes, "achieved_gbs": sample_bytes / (kern_ms * 1e-3) / 1e9,
