@@ -93,7 +93,7 @@ struct RhsOut {  // optional diagnostics (dict of spacecraft_model.py:472-480)
 // iteration and ONE inverse-trig call (the returned angle) instead of 2 + n atan2 and 1 + n
 // sincos.  Only |lat| is needed by the density (spacecraft_model.py:76).
 //   p2 = x^2 + y^2, inv_p = 1/sqrt(p2) are passed in (shared with the caller).
-RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
+RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, double &B_out) {
     const double p = p2 * inv_p;
     // theta = atan2(z R, p (1 - e2 R)) -> (sin, cos) by normalisation
     const double ta = z * KC(earth_r), tb = p * KC(one_m_e2r);
@@ -118,8 +118,16 @@ RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
             }
         }
     }
+    A_out = A; B_out = B;
+}
+RB_HD double pair_abs_latitude_deg(double A, double B) {
     const double nr = rb_rsqrt(fma(A, A, B * B));
     return rb_atan2_unit(fabs(A) * nr, B * nr) * KC(rad2deg);
+}
+RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
+    double A, B;
+    geodetic_pair(p2, inv_p, z, A, B);
+    return pair_abs_latitude_deg(A, B);
 }
 
 // Density (and temperature) -- atmosphere_model / simplified_nrlmsise_00 / solar_activity_factor
@@ -180,30 +188,34 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         ax += jx; ay += jy; az += jz;
         if (DIAG) { diag->a_j2[0] = jx; diag->a_j2[1] = jy; diag->a_j2[2] = jz; }
     }
-    // third bodies, :355-363 : k d/|d|^3 - k s/|s|^3 (the second term is time-only -> table)
-    {
-        const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
-        const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-        const double k3 = KC(moon_k) * (id * id * id);
-        const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
-        ax += mx; ay += my; az += mz;
-        if (DIAG) { diag->a_moon[0] = mx; diag->a_moon[1] = my; diag->a_moon[2] = mz; }
-    }
-    {
-        const double dx = e[E_SUN + 0] - x, dy = e[E_SUN + 1] - y, dz = e[E_SUN + 2] - z;
-        const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-        const double k3 = KC(sun_k) * (id * id * id);
-        const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
-        ax += sx; ay += sy; az += sz;
-        if (DIAG) { diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz; }
-    }
     // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
     // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
     {
         const double altitude = rn - KC(earth_r);
         // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
         const double ip = rb_rsqrt(p2);
-        const double lat_deg = geodetic_abs_latitude_deg(p2, ip, z);
+        double gA, gB;
+        geodetic_pair(p2, ip, z, gA, gB);
+        // independent third-body chains placed here so that they fill the latency of the serial
+        // latitude -> density -> drag tail
+        // third bodies, :355-363 : k d/|d|^3 - k s/|s|^3 (the second term is time-only -> table)
+        {
+            const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
+            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+            const double k3 = KC(moon_k) * (id * id * id);
+            const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
+            ax += mx; ay += my; az += mz;
+            if (DIAG) { diag->a_moon[0] = mx; diag->a_moon[1] = my; diag->a_moon[2] = mz; }
+        }
+        {
+            const double dx = e[E_SUN + 0] - x, dy = e[E_SUN + 1] - y, dz = e[E_SUN + 2] - z;
+            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+            const double k3 = KC(sun_k) * (id * id * id);
+            const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
+            ax += sx; ay += sy; az += sz;
+            if (DIAG) { diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz; }
+        }
+        const double lat_deg = pair_abs_latitude_deg(gA, gB);
         double T;
         const double rho = density(altitude, lat_deg, e[E_SOLAR], T);
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
