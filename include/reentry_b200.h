@@ -98,6 +98,15 @@ int32_t rb_initial_states(rb_ctx *ctx, int64_t n, const double *v, const double 
                           const double *alt, const double *azimuth, const double *gamma, double gmst,
                           double *y0, int64_t y0_traj_stride, int64_t y0_comp_stride, void *stream);
 
+/* ---- Monte-Carlo dispersions generated on the device (new, the reference
+ * propagates one trajectory): Philox4x32-10 keyed by `seed`, counter = (first_index + i, draw),
+ * Box-Muller normals z[6]; (v, lat, lon, alt, azimuth, gamma)[c] = nominal6[c] + sigma6[c]*z[c], then
+ * get_initial_state.  The result for trajectory first_index + i does not depend on how the ensemble
+ * is sharded.  nominal6 / sigma6 are HOST arrays; params (device SoA [6][n]) may be NULL. */
+int32_t rb_dispersed_initial_states(rb_ctx *ctx, int64_t n, int64_t first_index, uint64_t seed,
+                                    const double *nominal6, const double *sigma6, double gmst, double *params,
+                                    double *y0, int64_t y0_traj_stride, int64_t y0_comp_stride, void *stream);
+
 /* ---- propagation ------------------------------------------------------------------- */
 typedef struct rb_in {
     int64_t n;               /* trajectories */
@@ -159,6 +168,24 @@ int32_t rb_equations_of_motion(rb_ctx *ctx, int64_t n, const double *t, const do
                                double gmst0, const double *cd, const double *area, const double *mass,
                                double cd_scalar, double area_scalar, double mass_scalar, double *out,
                                void *stream);
+
+/* ---- ground-track post-pass: app.py:225-243 (per-sample ECI -> ECEF ->
+ * ecef_to_geodetic, coordinate_converter.py:81-96), app.py:302-308 (cumulative haversine down-range,
+ * cc:125-136), spacecraft_visualization.py:562-577 (crossings of an altitude threshold, 100 km in the
+ * app).  samples as written by rb_propagate; sample k is at t0 + k*sample_dt.  Outputs (device, any
+ * may be NULL): geo [n_out][3][n] = lat deg, lon deg, h m; downrange [n_out][n] m; time / down-range
+ * of the first crossing [n] (NaN = none); number of crossings [n]. */
+int32_t rb_ground_track(rb_ctx *ctx, int64_t n, int64_t n_out, const double *samples, int64_t sample_stride,
+                        int64_t field_stride, const int32_t *n_samples, double t0, double sample_dt, double gmst0,
+                        double threshold, double *geo, double *downrange, double *cross_time,
+                        double *cross_downrange, int32_t *n_cross, void *stream);
+
+/* Geodetic impact (or end) point of every trajectory from rb_propagate's summaries: final_state SoA
+ * [6][n] taken at impact_time[i] (impacted) or t_end; out SoA [3][n] = lat deg, lon deg, h m.  (The
+ * app's own touchdown read-out, app.py:322-327, feeds un-rotated ECI coordinates to ecef_to_geodetic;
+ * this is the rotated -- correct -- form, equal to the app's geodetic_coords[-1] convention.) */
+int32_t rb_impact_points(rb_ctx *ctx, int64_t n, const double *final_state, const double *impact_time,
+                         const uint8_t *status, double t_end, double gmst0, double *out, void *stream);
 
 /* ---- host-buffer convenience (the end-to-end call of a ctypes / cgo style binding) ----
  * Everything is HOST memory (pinned memory from rb_host_alloc makes the copies asynchronous):

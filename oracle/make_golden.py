@@ -15,6 +15,8 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
   c4_geo_heo.npz       4 GEO + 4 HEO, dt = 60 s, 6 days, stride 1440, O3
   edge.npz             edge cases: start below the event altitude, steep entry, per-trajectory
                        Cd/A/m, event in the first step, no event within the horizon
+  ground_track.npz     N2: per-sample geodetic coordinates, cumulative haversine down-range and
+                       100 km crossings of four O3 trajectories, from the reference's own functions
   recorded_trajectory.json   first samples of the trajectory embedded in temperature_model.py:104-105
 
     python oracle/make_golden.py        # ~2-3 min (numba JIT of the reference leaves dominates)
@@ -252,6 +254,34 @@ def edge_cases(const):
                 y0=y0, ys=o3["ys"], impact_step=o3["impact_step"], t_event=o3["t_event"], y_event=o3["y_event"])
 
 
+def ground_track(cc, const):
+    """N2: the app's post-pass (app.py:225-243 ECI->ECEF->geodetic, :302-308 cumulative haversine,
+    spacecraft_visualization.py:562-577 crossing finder restated inline -- that module imports plotly)
+    evaluated with the reference's own functions on O3 trajectories."""
+    c1 = np.load(os.path.join(GOLD, "c1_single.npz"))
+    c2 = np.load(os.path.join(GOLD, "c2_mc.npz"))
+    cases = [(c1["o3_ys"][:int(c1["o3_impact_step"])], 0.0, 1.0, 0.37)]
+    for j in (0, 5, 17):
+        ys = c2["ys"][j]
+        ys = ys[~np.isnan(ys[:, 0])]
+        cases.append((ys, 0.0, float(c2["dt"]) * int(c2["stride"]), 2.1 + j))
+    out = {}
+    for k, (ys, t0, dts, gmst0) in enumerate(cases):
+        t = t0 + dts * np.arange(len(ys))
+        geo = np.array([cc.ecef_to_geodetic(*cc.eci_to_ecef(np.ascontiguousarray(r), gmst0 + const.EARTH_OMEGA * tt))
+                        for r, tt in zip(ys[:, :3], t)])
+        dr = [0.0]
+        for i in range(1, len(geo)):
+            dr.append(dr[-1] + cc.haversine_distance(geo[i - 1, 0], geo[i - 1, 1], geo[i, 0], geo[i, 1]))
+        alt = np.array([np.sqrt(r[0] ** 2 + r[1] ** 2 + r[2] ** 2) - const.EARTH_R for r in ys[:, :3]])
+        cross = [i for i in range(1, len(alt)) if (alt[i] >= 100000 and alt[i - 1] < 100000) or
+                 (alt[i] <= 100000 and alt[i - 1] > 100000)]
+        out.update({f"ys_{k}": ys, f"t_{k}": t, f"gmst0_{k}": gmst0, f"geo_{k}": geo, f"downrange_{k}": np.array(dr),
+                    f"altitude_{k}": alt, f"cross_{k}": np.array(cross, dtype=np.int64)})
+    out["n_cases"] = len(cases)
+    return out
+
+
 def recorded_trajectory():
     """First samples of the trajectory recorded inside temperature_model.py:104-105 (10 s spacing;
     app defaults v=7540, 45N, 75W, 500 km, az 90, gamma -2).  Sample 0 pins get_initial_state
@@ -269,6 +299,9 @@ def recorded_trajectory():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     sm, cc, const = R.load()
+    if "--only-ground-track" in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
+        return
     import scipy, numba  # noqa
     meta = dict(generated_by="oracle/make_golden.py", numpy=np.__version__, scipy=scipy.__version__,
                 numba=numba.__version__, epoch_jd=EPOCH_JD, jd_star=JD_STAR)
@@ -285,6 +318,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "c4_geo_heo.npz"), **c4_geo_heo(const))
     print("c3/c4 done")
     np.savez_compressed(os.path.join(GOLD, "edge.npz"), **edge_cases(const))
+    np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
     with open(os.path.join(GOLD, "recorded_trajectory.json"), "w") as f:
         json.dump(recorded_trajectory(), f)
     print("wrote", sorted(os.listdir(GOLD)))

@@ -50,6 +50,8 @@ def lib():
         _lib.rbo_solar_factor_time.restype = C.c_double
         _lib.rbo_propagate.restype = C.c_int
         _lib.rbo_max_threads.restype = C.c_int
+        _lib.rbo_haversine_distance.restype = C.c_double
+        _lib.rbo_ground_track.restype = C.c_int
     return _lib
 
 
@@ -188,3 +190,33 @@ def propagate(y0, Cd, A, m, epoch_jd, gmst0, t0, dt, n_steps, stride=1, want_sam
         P(final_state), P(status), P(n_samples), C.c_int(n_threads))
     return dict(samples=samples, impact_step=impact_step, impact_time=impact_time, final_state=final_state,
                 status=status, n_samples=n_samples, threads=used)
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+    lib().rbo_philox4x32_10(c, k, o)
+    return [int(x) for x in o]
+
+
+def dispersed_params(n, seed, nominal, sigma, first_index=0):
+    """N3 generator spec (counter-based): params [n, 6] = nominal + sigma * z."""
+    out = np.empty((n, 6))
+    lib().rbo_dispersed_params(C.c_int64(n), C.c_int64(first_index), C.c_uint64(seed), (C.c_double * 6)(*nominal),
+                               (C.c_double * 6)(*sigma), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def haversine_distance(lat1, lon1, lat2, lon2):
+    return lib().rbo_haversine_distance(*[C.c_double(float(x)) for x in (lat1, lon1, lat2, lon2)])
+
+
+def ground_track(r_eci, t, altitude, gmst0, threshold=100000.0):
+    """app.py:225-243, :302-309 for one trajectory: r_eci [n,3].  Returns geo [n,3] (lat deg, lon deg, h),
+    downrange [n], crossing indices."""
+    r = np.ascontiguousarray(r_eci, dtype=np.float64); n = r.shape[0]
+    t = np.ascontiguousarray(t, dtype=np.float64); alt = np.ascontiguousarray(altitude, dtype=np.float64)
+    geo = np.empty((n, 3)); dr = np.empty(n); ci = np.empty(64, dtype=np.int64)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    nc = lib().rbo_ground_track(C.c_int64(n), P(r), P(t), P(alt), C.c_double(gmst0), C.c_double(threshold), P(geo), P(dr),
+                                P(ci), C.c_int(64))
+    return geo, dr, ci[:min(nc, 64)].copy()

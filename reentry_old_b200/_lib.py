@@ -58,6 +58,7 @@ SIGNATURES = {
     "rb_build_time_table": (i32, [f64, f64, f64, f64, i64, vp, i32]),
     "rb_ctx_set_time_table": (i32, [vp, vp, i64, f64, f64, vp]),
     "rb_initial_states": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, f64, vp, i64, i64, vp]),
+    "rb_dispersed_initial_states": (i32, [vp, i64, i64, C.c_uint64, vp, vp, f64, vp, vp, i64, i64, vp]),
     "rb_propagate": (i32, [vp, C.POINTER(RbIn), C.POINTER(RbRun), C.POINTER(RbOut), vp]),
     "rb_ctx_stats": (i32, [vp, C.POINTER(RbStats)]),
     "rb_equations_of_motion": (i32, [vp, i64, vp, vp, f64, f64, vp, vp, vp, f64, f64, f64, vp, vp]),
@@ -65,6 +66,8 @@ SIGNATURES = {
                                 vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]),
     "rb_host_alloc": (vp, [i64]),
     "rb_host_free": (None, [vp]),
+    "rb_ground_track": (i32, [vp, i64, i64, vp, i64, i64, vp, f64, f64, f64, f64, vp, vp, vp, vp, vp, vp]),
+    "rb_impact_points": (i32, [vp, i64, vp, vp, vp, f64, f64, vp, vp]),
     "rb_math_probe": (i32, [vp, i32, i64, vp, vp, vp, vp]),
     "rb_fp64_peak_probe": (i32, [vp, f64, C.POINTER(f64), vp]),
 }

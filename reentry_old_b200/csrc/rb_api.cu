@@ -204,6 +204,21 @@ int32_t rb_initial_states(rb_ctx *ctx, int64_t n, const double *v, const double 
     return RB_OK;
 }
 
+int32_t rb_dispersed_initial_states(rb_ctx *ctx, int64_t n, int64_t first_index, uint64_t seed, const double *nominal6,
+                                    const double *sigma6, double gmst, double *params, double *y0,
+                                    int64_t y0_traj_stride, int64_t y0_comp_stride, void *stream) {
+    if (!ctx || n < 0 || first_index < 0 || !nominal6 || !sigma6 || !y0) return RB_ERR_INVALID_ARG;
+    if (n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    DispersionParams dp;
+    for (int c = 0; c < 6; ++c) { dp.nominal[c] = nominal6[c]; dp.sigma[c] = sigma6[c]; }
+    const int B = 256;
+    k_dispersed_states<<<(unsigned)((n + B - 1) / B), B, 0, (cudaStream_t)stream>>>(n, first_index, seed, dp, gmst, params, y0,
+                                                                                   y0_traj_stride, y0_comp_stride);
+    CK(cudaGetLastError());
+    return RB_OK;
+}
+
 int32_t rb_equations_of_motion(rb_ctx *ctx, int64_t n, const double *t, const double *y, double epoch_jd, double gmst0,
                                const double *cd, const double *area, const double *mass, double cd_scalar,
                                double area_scalar, double mass_scalar, double *out, void *stream) {
@@ -525,6 +540,32 @@ void *rb_host_alloc(int64_t bytes) {
 }
 void rb_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ N2: ground track
+int32_t rb_ground_track(rb_ctx *ctx, int64_t n, int64_t n_out, const double *samples, int64_t sample_stride,
+                        int64_t field_stride, const int32_t *n_samples, double t0, double sample_dt, double gmst0,
+                        double threshold, double *geo, double *downrange, double *cross_time, double *cross_downrange,
+                        int32_t *n_cross, void *stream) {
+    if (!ctx || n < 0 || n_out < 0 || !samples) return RB_ERR_INVALID_ARG;
+    if (n == 0 || n_out == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    GroundTrackParams p{n, n_out, samples, sample_stride, field_stride, n_samples, t0, sample_dt, gmst0, threshold,
+                        geo, downrange, cross_time, cross_downrange, n_cross};
+    k_ground_track<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return RB_OK;
+}
+
+int32_t rb_impact_points(rb_ctx *ctx, int64_t n, const double *final_state, const double *impact_time,
+                         const uint8_t *status, double t_end, double gmst0, double *out, void *stream) {
+    if (!ctx || n < 0 || !final_state || !status || !out) return RB_ERR_INVALID_ARG;
+    if (n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    k_impact_points<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, final_state, impact_time, status, t_end,
+                                                                                  gmst0, out);
+    CK(cudaGetLastError());
+    return RB_OK;
 }
 
 // ------------------------------------------------------------------ math self-test

@@ -590,32 +590,83 @@ RB_HD void time_entry(double t, double epoch0, double gmst0, double e[ENTRY_DOUB
 
 // ---------------------------------------------------------------- batched get_initial_state
 // spacecraft_model.py:412-435 with geodetic_to_spheroid (cc:71-79), enu_to_ecef (cc:105-116), ecef_to_eci (cc:50-68)
-__global__ void k_initial_states(int64_t n, const double *v, const double *lat, const double *lon, const double *alt,
-                                 const double *az, const double *gam, double gmst, double *y0, int64_t ts, int64_t cs) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double la = RB_DEG_TO_RAD * lat[i], lo = RB_DEG_TO_RAD * lon[i];
+__device__ __forceinline__ void initial_state(double v, double lat, double lon, double alt, double az, double gam,
+                                              double sg, double cg, double y[6]) {
+    const double la = RB_DEG_TO_RAD * lat, lo = RB_DEG_TO_RAD * lon;
     double sla, cla, slo, clo;
     sincos(la, &sla, &cla);
     sincos(lo, &slo, &clo);
     const double N = RB_EARTH_R / sqrt(1 - RB_EARTH_E2 * (sla * sla));
-    const double h = alt[i];
-    const double xe = (N + h) * cla * clo, ye = (N + h) * cla * slo, ze = ((1 - RB_EARTH_E2) * N + h) * sla;
+    const double xe = (N + alt) * cla * clo, ye = (N + alt) * cla * slo, ze = ((1 - RB_EARTH_E2) * N + alt) * sla;
     double saz, caz, sga, cga;
-    sincos(RB_DEG_TO_RAD * az[i], &saz, &caz);
-    sincos(RB_DEG_TO_RAD * gam[i], &sga, &cga);
-    const double ve = v[i] * saz * cga, vn = v[i] * caz * cga, vu = v[i] * sga;
+    sincos(RB_DEG_TO_RAD * az, &saz, &caz);
+    sincos(RB_DEG_TO_RAD * gam, &sga, &cga);
+    const double ve = v * saz * cga, vn = v * caz * cga, vu = v * sga;
     const double vxe = -slo * ve + -sla * clo * vn + cla * clo * vu;
     const double vye = clo * ve + -sla * slo * vn + cla * slo * vu;
     const double vze = cla * vn + sla * vu;
-    double sg, cg;
+    y[0] = cg * xe - sg * ye; y[1] = sg * xe + cg * ye; y[2] = ze;
+    y[3] = cg * vxe - sg * vye; y[4] = sg * vxe + cg * vye; y[5] = vze;
+}
+
+__global__ void k_initial_states(int64_t n, const double *v, const double *lat, const double *lon, const double *alt,
+                                 const double *az, const double *gam, double gmst, double *y0, int64_t ts, int64_t cs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sg, cg, y[6];
     sincos(gmst, &sg, &cg);
-    y0[i * ts + 0 * cs] = cg * xe - sg * ye;
-    y0[i * ts + 1 * cs] = sg * xe + cg * ye;
-    y0[i * ts + 2 * cs] = ze;
-    y0[i * ts + 3 * cs] = cg * vxe - sg * vye;
-    y0[i * ts + 4 * cs] = sg * vxe + cg * vye;
-    y0[i * ts + 5 * cs] = vze;
+    initial_state(v[i], lat[i], lon[i], alt[i], az[i], gam[i], sg, cg, y);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) y0[i * ts + c * cs] = y[c];
+}
+
+// ---------------------------------------------------------------- N3: counter-based dispersion generator
+// Philox4x32-10 keyed by the seed, counter = (global trajectory index, draw): the dispersion of
+// trajectory i does not depend on how the ensemble is sharded over GPUs.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct DispersionParams {
+    double nominal[6], sigma[6];
+};
+
+__global__ void k_dispersed_states(int64_t n, int64_t first_index, uint64_t seed, DispersionParams dp, double gmst,
+                                   double *params /* SoA [6][n] or NULL */, double *y0, int64_t ts, int64_t cs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t idx = (uint64_t)(first_index + i);
+    double q[6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)d, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const double u1 = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u2 = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs2;
+        sincos(2.0 * RB_PI * u2, &sn, &cs2);
+        q[2 * d] = dp.nominal[2 * d] + dp.sigma[2 * d] * (rad * cs2);
+        q[2 * d + 1] = dp.nominal[2 * d + 1] + dp.sigma[2 * d + 1] * (rad * sn);
+    }
+    if (params) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) params[c * n + i] = q[c];
+    }
+    double sg, cg, y[6];
+    sincos(gmst, &sg, &cg);
+    initial_state(q[0], q[1], q[2], q[3], q[4], q[5], sg, cg, y);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) y0[i * ts + c * cs] = y[c];
 }
 
 // ---------------------------------------------------------------- diagnostics (equations_of_motion dict)
@@ -645,6 +696,70 @@ __global__ void __launch_bounds__(128) k_eom(int64_t n, const double *t, const d
     o[19 * n] = d.latitude_deg;
     o[20 * n] = d.rho;
     o[21 * n] = d.T;
+}
+
+// ---------------------------------------------------------------- N2: ground-track post-pass
+// app.py:225-243 (ECI -> ECEF -> geodetic per sample), :302-308 (cumulative haversine down-range),
+// spacecraft_visualization.py:562-577 (altitude-threshold crossings).  One thread per trajectory walks
+// its samples in time order (the down-range sum is sequential); rows are [k][field][traj] -> coalesced.
+struct GroundTrackParams {
+    int64_t n, n_out;
+    const double *samples;
+    int64_t sample_stride, field_stride;
+    const int32_t *n_samples;   // valid samples per trajectory, or NULL (= n_out)
+    double t0, sample_dt, gmst0, threshold;
+    double *geo;                // [n_out][3][n] lat deg, lon deg, h; or NULL
+    double *downrange;          // [n_out][n] or NULL
+    double *cross_time;         // [n] time of the first threshold crossing (NaN none) or NULL
+    double *cross_downrange;    // [n] or NULL
+    int32_t *n_cross;           // [n] number of crossings or NULL
+};
+
+__global__ void __launch_bounds__(128) k_ground_track(const GroundTrackParams p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const int ns = p.n_samples ? p.n_samples[i] : (int)p.n_out;
+    double lat0 = 0, lon0 = 0, dr = 0.0, alt_prev = 0, ct = nan(""), cd = nan("");
+    int nc = 0;
+    for (int k = 0; k < ns; ++k) {
+        const double *s = p.samples + k * p.sample_stride + i;
+        const double x = s[0], y = s[p.field_stride], z = s[2 * p.field_stride], alt = s[6 * p.field_stride];
+        const double t = p.t0 + p.sample_dt * k;
+        double sg, cg;
+        sincos(p.gmst0 + RB_EARTH_OMEGA * t, &sg, &cg);           // app.py:225
+        const double xe = cg * x + sg * y, ye = cg * y - sg * x;   // eci_to_ecef
+        double lat, lon, h;
+        geodetic_full(xe, ye, z, lat, lon, h);
+        if (k > 0) dr += haversine(lat0, lon0, lat, lon);
+        if (k > 0 && ((alt >= p.threshold && alt_prev < p.threshold) || (alt <= p.threshold && alt_prev > p.threshold))) {
+            if (nc == 0) { ct = t; cd = dr; }
+            ++nc;
+        }
+        if (p.geo) {
+            double *g = p.geo + (int64_t)k * 3 * p.n + i;
+            g[0] = lat; g[p.n] = lon; g[2 * p.n] = h;
+        }
+        if (p.downrange) p.downrange[(int64_t)k * p.n + i] = dr;
+        lat0 = lat; lon0 = lon; alt_prev = alt;
+    }
+    if (p.cross_time) p.cross_time[i] = ct;
+    if (p.cross_downrange) p.cross_downrange[i] = cd;
+    if (p.n_cross) p.n_cross[i] = nc;
+}
+
+// geodetic impact point (or end point) of every trajectory: final_state SoA [6][n] at time
+// impact_time[i] (impacted) or t_end (others); out SoA [3][n] = lat deg, lon deg, h
+__global__ void k_impact_points(int64_t n, const double *final_state, const double *impact_time, const uint8_t *status,
+                                double t_end, double gmst0, double *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t = (status[i] == RB_TRAJ_IMPACTED && impact_time && impact_time[i] == impact_time[i]) ? impact_time[i] : t_end;
+    double sg, cg;
+    sincos(gmst0 + RB_EARTH_OMEGA * t, &sg, &cg);
+    const double x = final_state[i], y = final_state[n + i], z = final_state[2 * n + i];
+    double lat, lon, h;
+    geodetic_full(cg * x + sg * y, cg * y - sg * x, z, lat, lon, h);
+    out[i] = lat; out[n + i] = lon; out[2 * n + i] = h;
 }
 
 // ---------------------------------------------------------------- self-test of rb_math.cuh

@@ -130,6 +130,32 @@ RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
     return pair_abs_latitude_deg(A, B);
 }
 
+// Full ecef_to_geodetic (coordinate_converter.py:81-96): signed latitude, longitude (degrees) and
+// the height h = p / cos(lat) - N of the RETURNED iterate, for the ground-track post-pass (N2).
+RB_HD void geodetic_full(double x, double y, double z, double &lat_deg, double &lon_deg, double &h) {
+    const double p2 = fma(x, x, y * y);
+    const double ip = rb_rsqrt(p2);
+    double A, B;
+    geodetic_pair(p2, ip, z, A, B);
+    const double n2 = fma(A, A, B * B);
+    const double nr = rb_rsqrt(n2);
+    const double a = rb_atan2_unit(fabs(A) * nr, B * nr) * KC(rad2deg);
+    lat_deg = (A < 0.0) ? -a : a;
+    lon_deg = atan2(y, x) * KC(rad2deg);
+    // N = R / sqrt(1 - e2 sin^2) = R sqrt(n2) / sqrt(B^2 + (1 - e2) A^2);  p / cos(lat) = p sqrt(n2) / B
+    const double sn = n2 * nr;  // sqrt(n2)
+    h = p2 * ip * sn * rb_rcp(B) - KC(earth_r) * sn * rb_rsqrt(fma(B, B, KC(one_m_e2) * (A * A)));
+}
+
+// haversine_distance, coordinate_converter.py:125-136 (degrees in, metres out)
+RB_HD double haversine(double lat1, double lon1, double lat2, double lon2) {
+    const double d2r = RB_PI / 180.0;
+    const double la1 = lat1 * d2r, la2 = lat2 * d2r;
+    const double sdl = sin((la2 - la1) * 0.5), sdo = sin((lon2 * d2r - lon1 * d2r) * 0.5);
+    const double a = sdl * sdl + cos(la1) * cos(la2) * (sdo * sdo);
+    return KC(earth_r) * (2.0 * atan2(sqrt(a), sqrt(1.0 - a)));
+}
+
 // Density (and temperature) -- atmosphere_model / simplified_nrlmsise_00 / solar_activity_factor
 // (spacecraft_model.py:181-188, :71-99, :148-168, :110-127).  solar_time = time-only part of the
 // solar factor from the time table.  The two exponentials of the top layer (:84 and :89) are

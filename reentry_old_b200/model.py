@@ -203,6 +203,24 @@ class SpacecraftModel:
                                             y0.data_ptr(), 6, 1, stream), "rb_initial_states")
         return y0
 
+    def get_dispersed_initial_states(self, n, seed, nominal, sigma, first_index=0, gmst=0.0, return_params=False):
+        """Monte-Carlo initial states generated on the device (counter-based Philox4x32-10; the
+        state of trajectory first_index + i is independent of sharding).  nominal / sigma are the six
+        launch-geometry values (v, lat, lon, alt, azimuth, gamma) and their 1-sigma dispersions."""
+        torch = _torch()
+        ctx = self._ctx()
+        dev = f"cuda:{ctx.device}"
+        y0 = torch.empty((n, 6), dtype=torch.float64, device=dev)
+        params = torch.empty((6, n), dtype=torch.float64, device=dev) if return_params else None
+        nom = (C.c_double * 6)(*[float(x) for x in nominal])
+        sig = (C.c_double * 6)(*[float(x) for x in sigma])
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.check(ctx.lib.rb_dispersed_initial_states(ctx.handle, int(n), int(first_index), int(seed), C.addressof(nom),
+                                                      C.addressof(sig), float(gmst),
+                                                      None if params is None else params.data_ptr(), y0.data_ptr(), 6, 1,
+                                                      stream), "rb_dispersed_initial_states")
+        return (y0, params.t()) if return_params else y0
+
     # ------------------------------------------------------------- equations_of_motion
     def equations_of_motion_batch(self, t, y, Cd=None, A=None, m=None):
         """Device evaluation of the RHS dict for N (t, y) pairs.  t [N]; y [N,6] -> dict of CUDA tensors."""
@@ -292,6 +310,39 @@ class SpacecraftModel:
         return EnsembleResult(t=t, samples=samples, final_state=final_state, impact_step=impact_step,
                               impact_time=impact_time, status=status, n_samples=n_samples, dt=float(dt),
                               out_stride=int(out_stride), n_steps=int(n_steps), stats=ctx.stats())
+
+    # ------------------------------------------------------------- ground track (N2)
+    def ground_track(self, res: EnsembleResult, threshold=100000.0, t0=0.0):
+        """The app's post-pass for every trajectory of an ensemble (app.py:225-243, :302-309): dict of
+        CUDA tensors geo [n_out, 3, N] (lat deg, lon deg, h), downrange [n_out, N], crossing_time [N],
+        crossing_downrange [N], n_crossings [N] (NaN after the event / when there is no crossing)."""
+        torch = _torch()
+        ctx = self._ctx()
+        n_out, _, n = res.samples.shape
+        dev = res.samples.device
+        geo = torch.full((n_out, 3, n), float("nan"), dtype=torch.float64, device=dev)
+        dr = torch.full((n_out, n), float("nan"), dtype=torch.float64, device=dev)
+        ct = torch.empty(n, dtype=torch.float64, device=dev)
+        cd = torch.empty(n, dtype=torch.float64, device=dev)
+        nc = torch.empty(n, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.check(ctx.lib.rb_ground_track(ctx.handle, n, n_out, res.samples.data_ptr(), L.RB_SAMPLE_FIELDS * n, n,
+                                          res.n_samples.data_ptr(), float(t0), res.dt * res.out_stride, self.gmst0,
+                                          float(threshold), geo.data_ptr(), dr.data_ptr(), ct.data_ptr(), cd.data_ptr(),
+                                          nc.data_ptr(), stream), "rb_ground_track")
+        return dict(geo=geo, downrange=dr, crossing_time=ct, crossing_downrange=cd, n_crossings=nc)
+
+    def impact_points(self, res: EnsembleResult, t0=0.0):
+        """Geodetic impact (or end) points [3, N] = lat deg, lon deg, h of an ensemble."""
+        torch = _torch()
+        ctx = self._ctx()
+        n = res.status.shape[0]
+        out = torch.empty((3, n), dtype=torch.float64, device=res.status.device)
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.check(ctx.lib.rb_impact_points(ctx.handle, n, res.final_state.data_ptr(), res.impact_time.data_ptr(),
+                                           res.status.data_ptr(), float(t0) + res.dt * res.n_steps, self.gmst0,
+                                           out.data_ptr(), stream), "rb_impact_points")
+        return out
 
     # ------------------------------------------------------------------ run_simulation
     def run_simulation(self, t_span, y0, t_eval, progress_callback=None, max_step=None):
