@@ -160,14 +160,24 @@ typedef struct rb_stats {
 int32_t rb_ctx_stats(const rb_ctx *ctx, rb_stats *out);
 
 /* ---- per-sample diagnostics: the dict of SpacecraftModel.equations_of_motion
- * (spacecraft_model.py:472-480) for n given (t, y) pairs; used for additional_data
- * (spacecraft_model.py:517-518).  t device [n]; y SoA [6][n]; out SoA [RB_DIAG_FIELDS][n]:
- * a_total[3], a_grav[3], a_j2[3], a_moon[3], a_sun[3], a_drag[3], altitude, latitude_deg, rho, T. */
-#define RB_DIAG_FIELDS 22
+ * (spacecraft_model.py:472-487) for n given (t, y) pairs; used for additional_data
+ * (spacecraft_model.py:517-518).  t device [n]; y SoA [6][n]; out SoA [rows][n]:
+ * a_total[3], a_grav[3], a_j2[3], a_moon[3], a_sun[3], a_drag[3], altitude, |latitude| deg, rho, T,
+ * |v_rel| (RB_DIAG_FIELDS = 23 rows), then -- when `thermal` is not NULL -- the six values of
+ * spacecraft_temperature (spacecraft_model.py:243-255, N1) in ITS return order Qc, Qr, Q_net, Q, T_s,
+ * dT (RB_THERMAL_FIELDS = 6 more rows; the reference's caller at :468 stores them under permuted
+ * names, which the Python mirror reproduces). */
+#define RB_DIAG_FIELDS 23
+#define RB_THERMAL_FIELDS 6
+typedef struct rb_thermal {
+    double capsule_length;          /* SpacecraftModel.height, spacecraft_model.py:396 */
+    double dt, iter_fact;           /* iterations = int(dt / iter_fact), :246 */
+    double thermal_conductivity, specific_heat_capacity, emissivity, ablation_efficiency; /* material, :405-408 */
+} rb_thermal;
 int32_t rb_equations_of_motion(rb_ctx *ctx, int64_t n, const double *t, const double *y, double epoch_jd,
                                double gmst0, const double *cd, const double *area, const double *mass,
-                               double cd_scalar, double area_scalar, double mass_scalar, double *out,
-                               void *stream);
+                               double cd_scalar, double area_scalar, double mass_scalar,
+                               const rb_thermal *thermal, double *out, void *stream);
 
 /* ---- ground-track post-pass: app.py:225-243 (per-sample ECI -> ECEF ->
  * ecef_to_geodetic, coordinate_converter.py:81-96), app.py:302-308 (cumulative haversine down-range,

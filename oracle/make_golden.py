@@ -17,6 +17,8 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
                        Cd/A/m, event in the first step, no event within the horizon
   ground_track.npz     N2: per-sample geodetic coordinates, cumulative haversine down-range and
                        100 km crossings of four O3 trajectories, from the reference's own functions
+  thermal.npz          N1: thermal entries of the unmodified equations_of_motion dict + direct
+                       spacecraft_temperature calls
   recorded_trajectory.json   first samples of the trajectory embedded in temperature_model.py:104-105
 
     python oracle/make_golden.py        # ~2-3 min (numba JIT of the reference leaves dominates)
@@ -282,6 +284,34 @@ def ground_track(cc, const):
     return out
 
 
+def thermal(sm, const):
+    """N1: thermal keys of the UNMODIFIED equations_of_motion dict (:468, :481-486) on reentry states, for two
+    (material, dt, iter_fact) settings, plus direct spacecraft_temperature calls on random inputs."""
+    rng = np.random.default_rng(21)
+    out = {}
+    keys = ["spacecraft_temperature", "spacecraft_heat_flux", "spacecraft_heat_flux_conduction",
+            "spacecraft_heat_flux_radiation", "spacecraft_heat_flux_total", "spacecraft_temperature_change"]
+    n = 96
+    alt = rng.uniform(20e3, 130e3, n)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    y = np.concatenate([u * (const.EARTH_R + alt)[:, None], rng.normal(size=(n, 3)) * 3500], axis=1)
+    t = rng.uniform(0, 5000, n)
+    for tag, (mat, dt, itf, Cd, A, m) in {"a": ([0.167, 1260, 0.9, 0.7], 10, 2, 1.3, 14.0, 5000.0),
+                                           "b": ([237, 903, 0.1, 0.1], 30, 4, 2.2, 20.0, 500.0)}.items():
+        mdl = sm.SpacecraftModel(Cd=Cd, A=A, m=m, epoch=R.Epoch(EPOCH_JD), gmst0=0.2, material=mat, dt=dt, iter_fact=itf)
+        rows = [mdl.equations_of_motion(ti, yi) for ti, yi in zip(t, y)]
+        for k in keys:
+            out[f"{tag}_{k}"] = np.array([float(r[k]) for r in rows])
+        out[f"{tag}_cfg"] = np.array(mat + [dt, itf, Cd, A, m, mdl.height], dtype=np.float64)
+    out.update(t=t, y=y, epoch_jd=EPOCH_JD, gmst0=0.2)
+    # direct calls
+    args = np.stack([rng.uniform(100, 8000, 64), rng.uniform(180, 300, 64), 10 ** rng.uniform(-6, 2, 64)], axis=1)
+    out["direct_args"] = args
+    out["direct"] = np.array([sm.spacecraft_temperature(np.array([a[0], 0.0, 0.0]), a[1], np.array([0.0, a[2], 0.0]), 2.7, 10,
+                                                        0.167, 1260, 0.9, 0.7, 2, 5000.0) for a in args], dtype=np.float64)
+    return out
+
+
 def recorded_trajectory():
     """First samples of the trajectory recorded inside temperature_model.py:104-105 (10 s spacing;
     app defaults v=7540, 45N, 75W, 500 km, az 90, gamma -2).  Sample 0 pins get_initial_state
@@ -299,6 +329,9 @@ def recorded_trajectory():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     sm, cc, const = R.load()
+    if "--only-thermal" in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
+        return
     if "--only-ground-track" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
         return
@@ -319,6 +352,7 @@ def main():
     print("c3/c4 done")
     np.savez_compressed(os.path.join(GOLD, "edge.npz"), **edge_cases(const))
     np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
+    np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
     with open(os.path.join(GOLD, "recorded_trajectory.json"), "w") as f:
         json.dump(recorded_trajectory(), f)
     print("wrote", sorted(os.listdir(GOLD)))

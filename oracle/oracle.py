@@ -220,3 +220,13 @@ def ground_track(r_eci, t, altitude, gmst0, threshold=100000.0):
     nc = lib().rbo_ground_track(C.c_int64(n), P(r), P(t), P(alt), C.c_double(gmst0), C.c_double(threshold), P(geo), P(dr),
                                 P(ci), C.c_int(64))
     return geo, dr, ci[:min(nc, 64)].copy()
+
+
+def spacecraft_temperature(v_norm, atmo_T, a_drag_norm, capsule_length, dt, thermal_conductivity, specific_heat_capacity,
+                           emissivity, ablation_efficiency, iter_fact=2, spacecraft_m=500):
+    """spacecraft_model.py:243-255; returns (Qc, Qr, Q_net, Q, T_s, dT) in the reference's return order."""
+    o = (C.c_double * 6)()
+    lib().rbo_spacecraft_temperature(*[C.c_double(float(x)) for x in (
+        v_norm, atmo_T, a_drag_norm, capsule_length, dt, thermal_conductivity, specific_heat_capacity, emissivity,
+        ablation_efficiency, iter_fact, spacecraft_m)], o)
+    return tuple(o)

@@ -17,7 +17,8 @@ RB_FLAG_NO_REFINE = 4
 RB_FLAG_PROFILE = 8
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
-RB_DIAG_FIELDS = 22
+RB_DIAG_FIELDS = 23
+RB_THERMAL_FIELDS = 6
 TRAJ_ALIVE, TRAJ_IMPACTED, TRAJ_NONFINITE = 0, 1, 2
 
 vp = C.c_void_p
@@ -42,6 +43,11 @@ class RbOut(C.Structure):
                 ("final_state", vp), ("impact_step", vp), ("impact_time", vp), ("status", vp), ("n_samples", vp)]
 
 
+class RbThermal(C.Structure):
+    _fields_ = [("capsule_length", f64), ("dt", f64), ("iter_fact", f64), ("thermal_conductivity", f64),
+                ("specific_heat_capacity", f64), ("emissivity", f64), ("ablation_efficiency", f64)]
+
+
 class RbStats(C.Structure):
     _fields_ = [("kernel_launches", i64), ("propagate_launches", i64), ("steps_enqueued", i64),
                 ("last_polled_live", i64), ("propagate_ms", f64)]
@@ -61,7 +67,7 @@ SIGNATURES = {
     "rb_dispersed_initial_states": (i32, [vp, i64, i64, C.c_uint64, vp, vp, f64, vp, vp, i64, i64, vp]),
     "rb_propagate": (i32, [vp, C.POINTER(RbIn), C.POINTER(RbRun), C.POINTER(RbOut), vp]),
     "rb_ctx_stats": (i32, [vp, C.POINTER(RbStats)]),
-    "rb_equations_of_motion": (i32, [vp, i64, vp, vp, f64, f64, vp, vp, vp, f64, f64, f64, vp, vp]),
+    "rb_equations_of_motion": (i32, [vp, i64, vp, vp, f64, f64, vp, vp, vp, f64, f64, f64, C.POINTER(RbThermal), vp, vp]),
     "rb_propagate_host": (i32, [vp, i64, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, f64, C.POINTER(RbRun),
                                 vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]),
     "rb_host_alloc": (vp, [i64]),

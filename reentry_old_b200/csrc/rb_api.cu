@@ -221,12 +221,19 @@ int32_t rb_dispersed_initial_states(rb_ctx *ctx, int64_t n, int64_t first_index,
 
 int32_t rb_equations_of_motion(rb_ctx *ctx, int64_t n, const double *t, const double *y, double epoch_jd, double gmst0,
                                const double *cd, const double *area, const double *mass, double cd_scalar,
-                               double area_scalar, double mass_scalar, double *out, void *stream) {
+                               double area_scalar, double mass_scalar, const rb_thermal *thermal, double *out,
+                               void *stream) {
     if (!ctx || n < 0 || !t || !y || !out) return RB_ERR_INVALID_ARG;
     if (n == 0) return RB_OK;
     CK(cudaSetDevice(ctx->device));
-    k_eom<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, t, y, epoch_jd, gmst0, cd, area, mass,
-                                                                         cd_scalar, area_scalar, mass_scalar, out);
+    Thermal th{};
+    if (thermal) {
+        if (!(thermal->iter_fact > 0)) return RB_ERR_INVALID_ARG;
+        th = Thermal{thermal->capsule_length, thermal->dt, thermal->thermal_conductivity, thermal->specific_heat_capacity,
+                     thermal->emissivity, thermal->ablation_efficiency, thermal->iter_fact};
+    }
+    k_eom<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, t, y, epoch_jd, gmst0, cd, area, mass, cd_scalar,
+                                                                         area_scalar, mass_scalar, thermal ? 1 : 0, th, out);
     CK(cudaGetLastError());
     return RB_OK;
 }

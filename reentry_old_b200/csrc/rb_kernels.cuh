@@ -672,14 +672,15 @@ __global__ void k_dispersed_states(int64_t n, int64_t first_index, uint64_t seed
 // ---------------------------------------------------------------- diagnostics (equations_of_motion dict)
 __global__ void __launch_bounds__(128) k_eom(int64_t n, const double *t, const double *y, double epoch_jd, double gmst0,
                                              const double *cd, const double *area, const double *mass, double cd_s,
-                                             double area_s, double mass_s, double *out) {
+                                             double area_s, double mass_s, int has_thermal, Thermal th, double *out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double e[ENTRY_DOUBLES];
     time_entry(t[i], epoch_jd, gmst0, e);
     double r[3] = {y[0 * n + i], y[1 * n + i], y[2 * n + i]};
     double v[3] = {y[3 * n + i], y[4 * n + i], y[5 * n + i]};
-    const Body body = make_body(cd ? cd[i] : cd_s, area ? area[i] : area_s, mass ? mass[i] : mass_s);
+    const double m_i = mass ? mass[i] : mass_s;
+    const Body body = make_body(cd ? cd[i] : cd_s, area ? area[i] : area_s, m_i);
     double a[3];
     RhsOut d;
     acceleration<true>(e, r, v, body, a, &d);
@@ -696,6 +697,13 @@ __global__ void __launch_bounds__(128) k_eom(int64_t n, const double *t, const d
     o[19 * n] = d.latitude_deg;
     o[20 * n] = d.rho;
     o[21 * n] = d.T;
+    o[22 * n] = d.v_rel_norm;
+    if (has_thermal) {
+        double q[6];
+        const double adn = sqrt(d.a_drag[0] * d.a_drag[0] + d.a_drag[1] * d.a_drag[1] + d.a_drag[2] * d.a_drag[2]);
+        spacecraft_temperature(d.v_rel_norm, d.T, adn, m_i, th, q);
+        for (int c = 0; c < 6; ++c) o[(23 + c) * n] = q[c];
+    }
 }
 
 // ---------------------------------------------------------------- N2: ground-track post-pass

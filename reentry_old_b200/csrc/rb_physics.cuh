@@ -76,8 +76,33 @@ RB_HD Body make_body(double cd, double area, double mass) { return Body{0.5 * cd
 
 struct RhsOut {  // optional diagnostics (dict of spacecraft_model.py:472-480)
     double a_grav[3], a_j2[3], a_moon[3], a_sun[3], a_drag[3];
-    double altitude, latitude_deg, rho, T;
+    double altitude, latitude_deg, rho, T, v_rel_norm;
 };
+
+// N1: heat_transfer / spacecraft_temperature (spacecraft_model.py:223-255), stateless per sample.
+// out = (Qc, Qr, Q_net, Q, T_s, dT) in the reference's RETURN order.
+struct Thermal {
+    double capsule_length, dt, thermal_conductivity, specific_heat_capacity, emissivity, ablation_efficiency, iter_fact;
+};
+RB_HD void spacecraft_temperature(double v_norm, double atmo_T, double a_drag_norm, double mass, const Thermal &th,
+                                  double out[6]) {
+    double T_s = atmo_T;
+    const int idt = (int)(th.dt / th.iter_fact);
+    const double dti = (double)idt;
+    for (int k = 0; k < 6; ++k) out[k] = nan("");
+    const double Q = th.ablation_efficiency * ((mass * a_drag_norm) * v_norm);
+    const double Ta2 = atmo_T * atmo_T, Ta4 = Ta2 * Ta2;
+    for (int it = 0; it < idt; ++it) {
+        const double Qc = th.thermal_conductivity * (T_s - atmo_T) / th.capsule_length;
+        const double Ts2 = T_s * T_s;
+        const double Qr = th.emissivity * 5.67e-8 * (Ts2 * Ts2 - Ta4);
+        const double Q_net = Q - Qc - Qr;
+        const double dT = Q_net / (mass * th.specific_heat_capacity) * dti;
+        out[0] = Qc; out[1] = Qr; out[2] = Q_net; out[3] = Q; out[5] = dT;
+        T_s += dT;
+    }
+    out[4] = T_s;
+}
 
 // |geodetic latitude| in DEGREES of an ECEF point: coordinate_converter.py:81-96 with its quirks
 // (theta built with (1 - e2*R); the loop tests |lat - lat_new| < 1e-6 BEFORE lat = lat_new, so
@@ -251,7 +276,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         ax += ddx; ay += ddy; az += ddz;
         if (DIAG) {
             diag->a_drag[0] = ddx; diag->a_drag[1] = ddy; diag->a_drag[2] = ddz;
-            diag->altitude = altitude; diag->latitude_deg = lat_deg; diag->rho = rho; diag->T = T;
+            diag->altitude = altitude; diag->latitude_deg = lat_deg; diag->rho = rho; diag->T = T; diag->v_rel_norm = vn;
         }
     }
     a[0] = ax; a[1] = ay; a[2] = az;

@@ -231,19 +231,30 @@ class SpacecraftModel:
         n = y.shape[0]
         t = self._dev(t, n)
         ysoa = y.t().contiguous()
-        out = torch.empty((L.RB_DIAG_FIELDS, n), dtype=torch.float64, device=y.device)
+        out = torch.empty((L.RB_DIAG_FIELDS + L.RB_THERMAL_FIELDS, n), dtype=torch.float64, device=y.device)
         arr = [None if a is None else self._dev(a, n) for a in (Cd, A, m)]
         ptr = [0 if a is None else a.data_ptr() for a in arr]
+        th = L.RbThermal(capsule_length=self.height, dt=float(self.dt), iter_fact=float(self.iter_fact),
+                         thermal_conductivity=float(self.thermal_conductivity),
+                         specific_heat_capacity=float(self.specific_heat_capacity), emissivity=float(self.emissivity),
+                         ablation_efficiency=float(self.ablation_efficiency))
         stream = torch.cuda.current_stream(ctx.device).cuda_stream
         ctx.check(ctx.lib.rb_equations_of_motion(ctx.handle, n, t.data_ptr(), ysoa.data_ptr(), self.epoch, self.gmst0,
                                                  ptr[0], ptr[1], ptr[2], float(self.Cd), float(self.A), float(self.m),
-                                                 out.data_ptr(), stream), "rb_equations_of_motion")
+                                                 C.byref(th), out.data_ptr(), stream), "rb_equations_of_motion")
         o = out
+        # thermal rows are spacecraft_temperature's RETURN order (Qc, Qr, Q_net, Q, T_s, dT); the reference
+        # unpacks them as q_gen, q_c, q_r, q_net, T_s, dT (spacecraft_model.py:468) and labels the dict from
+        # those names (:481-486) -- the permutation is reproduced so that the keys hold what the app gets
         return {
             "velocity": y[:, 3:6],
             "acceleration": o[0:3].t(), "gravitational_acceleration": o[3:6].t(), "J2_acceleration": o[6:9].t(),
             "moon_acceleration": o[9:12].t(), "sun_acceleration": o[12:15].t(), "drag_acceleration": o[15:18].t(),
-            "altitude": o[18], "latitude": o[19], "density": o[20], "temperature": o[21],
+            "altitude": o[18],
+            "spacecraft_temperature": o[27], "spacecraft_heat_flux": o[26], "spacecraft_heat_flux_conduction": o[24],
+            "spacecraft_heat_flux_radiation": o[25], "spacecraft_heat_flux_total": o[23],
+            "spacecraft_temperature_change": o[28],
+            "latitude": o[19], "density": o[20], "temperature": o[21], "relative_speed": o[22],
         }
 
     def equations_of_motion(self, t, y):
