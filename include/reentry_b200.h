@@ -60,6 +60,11 @@ typedef enum rb_traj_status {
 #define RB_FLAG_COMPACT 1u      /* order-preserving compaction of live trajectories between launches */
 #define RB_FLAG_EARLY_EXIT 2u   /* host polls the live count (2 launches behind) and stops when it is 0 */
 #define RB_FLAG_NO_REFINE 4u    /* skip the dense-output impact-time refinement (impact_time = NaN) */
+#define RB_FLAG_SKIP_NEGLIGIBLE_DRAG 16u /* above RB_NEGLIGIBLE_DRAG_ALTITUDE (400 km) the model's density
+                                   (<= 4e-49 kg/m^3, spacecraft_model.py:84-89) makes rho*bc*v^2 < 1e-40 m/s^2 for any
+                                   bc < 1e8 m^2/kg -- below one ulp of every other term -- so latitude, density and
+                                   drag are not evaluated there.  Off by default; orbit ensembles run ~2.5x faster */
+#define RB_NEGLIGIBLE_DRAG_ALTITUDE 400000.0
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */
 

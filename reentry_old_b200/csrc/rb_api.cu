@@ -301,6 +301,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
 
     StepParams sp{};
     sp.table = ctx->d_table; sp.out_stride = run->out_stride; sp.h = ctx->dt; sp.event_altitude = run->event_altitude;
+    sp.drag_skip_altitude = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) ? RB_NEGLIGIBLE_DRAG_ALTITUDE : 1e300;
     sp.state = out->final_state; sp.n = n;
     sp.cd = in->cd; sp.area = in->area; sp.mass = in->mass;
     sp.cd_s = in->cd_scalar; sp.area_s = in->area_scalar; sp.mass_s = in->mass_scalar;
@@ -361,6 +362,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
 
     RefineParams rp{};
     rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.event_altitude = run->event_altitude;
+    rp.drag_skip_altitude = sp.drag_skip_altitude;
     rp.state = out->final_state; rp.n = n;
     rp.cd = in->cd; rp.area = in->area; rp.mass = in->mass;
     rp.cd_s = in->cd_scalar; rp.area_s = in->area_scalar; rp.mass_s = in->mass_scalar;

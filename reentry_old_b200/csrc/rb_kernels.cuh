@@ -83,6 +83,7 @@ struct StepParams {
     int64_t out_stride;
     double h;
     double event_altitude;
+    double drag_skip_altitude;  // drag block is evaluated for altitude <= this (1e300 = always)
     // state / per-trajectory constants
     double *state;             // SoA [6][n]
     int64_t n;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
                 double a[3];
-                acceleration<false>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
+                acceleration<false>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr, p.drag_skip_altitude);
                 double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
                 Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
                 if (s == 6) {
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) k_scatter_live(const int32_t *l
 struct RefineParams {
     const double *table;
     int64_t table_steps;
-    double h, event_altitude;
+    double h, event_altitude, drag_skip_altitude;
     double *state;  // in: y at the start of the crossing step; out: dense-output state at the impact time
     int64_t n;
     const double *cd, *area, *mass;
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
                 ys[c] = (s == 0) ? y[c] : fma(dr, hh, fma(c_T.c[s] * h, y[3 + c], y[c]));
             }
             double a[3];
-            acceleration<false>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
+            acceleration<false>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr, p.drag_skip_altitude);
             K[s][0] = ys[3]; K[s][1] = ys[4]; K[s][2] = ys[5];
             K[s][3] = a[0];  K[s][4] = a[1];  K[s][5] = a[2];
         }

@@ -216,7 +216,7 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
 // e: time-table entry (16 doubles).  b.mass is used through b.bc = 0.5 Cd A / m.
 template <bool DIAG>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
-                        double a[3], RhsOut *diag) {
+                        double a[3], RhsOut *diag, double drag_skip_altitude = 1e300) {
     const double x = r[0], y = r[1], z = r[2];
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
@@ -239,16 +239,9 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         ax += jx; ay += jy; az += jz;
         if (DIAG) { diag->a_j2[0] = jx; diag->a_j2[1] = jy; diag->a_j2[2] = jz; }
     }
-    // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
-    // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
-    {
-        const double altitude = rn - KC(earth_r);
-        // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
-        const double ip = rb_rsqrt(p2);
-        double gA, gB;
-        geodetic_pair(p2, ip, z, gA, gB);
-        // independent third-body chains placed here so that they fill the latency of the serial
-        // latitude -> density -> drag tail
+    // third bodies as a lambda: evaluated inside the drag block (fills the latency of its serial tail)
+    // or on their own when the drag block is skipped
+    auto third_bodies = [&]() {
         // third bodies, :355-363 : k d/|d|^3 - k s/|s|^3 (the second term is time-only -> table)
         {
             const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
@@ -266,6 +259,16 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
             ax += sx; ay += sy; az += sz;
             if (DIAG) { diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz; }
         }
+    };
+    // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
+    // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
+    const double altitude = rn - KC(earth_r);
+    if (altitude <= drag_skip_altitude) {
+        // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
+        const double ip = rb_rsqrt(p2);
+        double gA, gB;
+        geodetic_pair(p2, ip, z, gA, gB);
+        third_bodies();
         const double lat_deg = pair_abs_latitude_deg(gA, gB);
         double T;
         const double rho = density(altitude, lat_deg, e[E_SOLAR], T);
@@ -277,6 +280,13 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         if (DIAG) {
             diag->a_drag[0] = ddx; diag->a_drag[1] = ddy; diag->a_drag[2] = ddz;
             diag->altitude = altitude; diag->latitude_deg = lat_deg; diag->rho = rho; diag->T = T; diag->v_rel_norm = vn;
+        }
+    } else {
+        // RB_FLAG_SKIP_NEGLIGIBLE_DRAG: above the threshold rho bc v^2 < 1e-40 m/s^2 (density tail of the model)
+        third_bodies();
+        if (DIAG) {
+            diag->a_drag[0] = diag->a_drag[1] = diag->a_drag[2] = 0.0;
+            diag->altitude = altitude; diag->latitude_deg = nan(""); diag->rho = 0.0; diag->T = KC(top_T); diag->v_rel_norm = nan("");
         }
     }
     a[0] = ax; a[1] = ay; a[2] = az;

@@ -153,6 +153,18 @@ def test_golden_orbits(Model, golden_dir, name):
     assert np.all(res.impact_step.cpu().numpy() == -1) and np.all(res.status.cpu().numpy() == 0)
 
 
+@pytest.mark.parametrize("name", ["c3_sso.npz", "c4_geo_heo.npz", "c2_mc.npz"])
+def test_skip_negligible_drag_is_exact(Model, torch, golden_dir, name):
+    """RB_FLAG_SKIP_NEGLIGIBLE_DRAG: bit-identical states above 400 km (the skipped term is < 1e-40 m/s^2),
+    and no effect at all on a reentry that stays below the threshold."""
+    g = np.load(os.path.join(golden_dir, name))
+    a = run_golden(Model, g, steps_per_launch=512)
+    b = run_golden(Model, g, steps_per_launch=512, skip_negligible_drag=True)
+    assert torch.equal(torch.nan_to_num(a.samples, nan=-1.0), torch.nan_to_num(b.samples, nan=-1.0))
+    assert torch.equal(a.final_state, b.final_state) and torch.equal(a.impact_step, b.impact_step)
+    compare_states(samples_np(b)[:, :, :6], g["ys"], name + " (skip)")
+
+
 def test_mc_vs_oracle_512(Model, oracle):
     """C2-shaped ensemble against the oracle on the same seeded inputs."""
     from reentry_old_b200.configs import reentry_dispersion_params
