@@ -100,8 +100,11 @@ int32_t rb_ctx_create(rb_ctx **out, int32_t device) {
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->poll_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) {
         ctx->events_ready = true;
-        e = cudaFuncSetAttribute(k_propagate<RB_BLOCK, RB_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)propagate_smem_bytes<RB_BLOCK>());
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)propagate_smem_bytes<RB_BLOCK>());
     }
     if (e != cudaSuccess) {
         fprintf(stderr, "rb_ctx_create: %s\n", cudaGetErrorString(e));
@@ -280,6 +283,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     const bool compact = (run->flags & RB_FLAG_COMPACT) != 0;
     const bool early = (run->flags & RB_FLAG_EARLY_EXIT) != 0;
     const bool profile = (run->flags & RB_FLAG_PROFILE) != 0;
+    const bool skip_drag = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) != 0;
     size_t prof_used = 0;
     auto prof_event = [&]() -> cudaEvent_t {
         if (prof_used == ctx->prof_events.size()) {
@@ -301,7 +305,6 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
 
     StepParams sp{};
     sp.table = ctx->d_table; sp.out_stride = run->out_stride; sp.h = ctx->dt; sp.event_altitude = run->event_altitude;
-    sp.drag_skip_altitude = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) ? RB_NEGLIGIBLE_DRAG_ALTITUDE : 1e300;
     sp.state = out->final_state; sp.n = n;
     sp.cd = in->cd; sp.area = in->area; sp.mass = in->mass;
     sp.cd_s = in->cd_scalar; sp.area_s = in->area_scalar; sp.mass_s = in->mass_scalar;
@@ -330,7 +333,8 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
         sp.live = ctx->d_live[cur];
         const unsigned grid = (unsigned)((live_bound + RB_BLOCK - 1) / RB_BLOCK);
         if (profile) CK(cudaEventRecord(prof_event(), stream));
-        k_propagate<RB_BLOCK, RB_MIN_BLOCKS><<<grid, RB_BLOCK, smem, stream>>>(sp);
+        if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, stream>>>(sp);
+        else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, stream>>>(sp);
         CK(cudaGetLastError());
         if (profile) CK(cudaEventRecord(prof_event(), stream));
         ctx->stats.kernel_launches++;
@@ -362,7 +366,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
 
     RefineParams rp{};
     rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.event_altitude = run->event_altitude;
-    rp.drag_skip_altitude = sp.drag_skip_altitude;
+    rp.skip_drag = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) ? 1 : 0;
     rp.state = out->final_state; rp.n = n;
     rp.cd = in->cd; rp.area = in->area; rp.mass = in->mass;
     rp.cd_s = in->cd_scalar; rp.area_s = in->area_scalar; rp.mass_s = in->mass_scalar;

@@ -83,7 +83,6 @@ struct StepParams {
     int64_t out_stride;
     double h;
     double event_altitude;
-    double drag_skip_altitude;  // drag block is evaluated for altitude <= this (1e300 = always)
     // state / per-trajectory constants
     double *state;             // SoA [6][n]
     int64_t n;
@@ -179,7 +178,7 @@ constexpr size_t propagate_smem_bytes() {
     return sizeof(double) * (2 * TILE_DOUBLES + K_SLOTS * K_ROWS * BLOCK) + 2 * sizeof(uint64_t);
 }
 
-template <int BLOCK, int MIN_BLOCKS>
+template <int BLOCK, int MIN_BLOCKS, bool SKIP>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
@@ -263,7 +262,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
                 double a[3];
-                acceleration<false>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr, p.drag_skip_altitude);
+                acceleration<false, SKIP>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
                 double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
                 Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
                 if (s == 6) {
@@ -406,7 +405,8 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) k_scatter_live(const int32_t *l
 struct RefineParams {
     const double *table;
     int64_t table_steps;
-    double h, event_altitude, drag_skip_altitude;
+    double h, event_altitude;
+    int skip_drag;
     double *state;  // in: y at the start of the crossing step; out: dense-output state at the impact time
     int64_t n;
     const double *cd, *area, *mass;
@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
                 ys[c] = (s == 0) ? y[c] : fma(dr, hh, fma(c_T.c[s] * h, y[3 + c], y[c]));
             }
             double a[3];
-            acceleration<false>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr, p.drag_skip_altitude);
+            if (p.skip_drag) acceleration<false, true>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
+            else acceleration<false, false>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
             K[s][0] = ys[3]; K[s][1] = ys[4]; K[s][2] = ys[5];
             K[s][3] = a[0];  K[s][4] = a[1];  K[s][5] = a[2];
         }

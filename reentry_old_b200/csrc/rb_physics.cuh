@@ -19,6 +19,8 @@
 
 namespace rb {
 
+constexpr double RB_NEGLIGIBLE_DRAG_ALTITUDE_ = 400000.0;  // == RB_NEGLIGIBLE_DRAG_ALTITUDE of the C ABI
+
 // time-table entry layout (include/reentry_b200.h)
 enum : int {
     E_SUN = 0, E_MOON = 3, E_SUN_IND = 6, E_MOON_IND = 9, E_CG = 12, E_SG = 13, E_SOLAR = 14, E_T = 15,
@@ -214,9 +216,11 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
 
 // Full acceleration of SpacecraftModel.equations_of_motion (spacecraft_model.py:437-470).
 // e: time-table entry (16 doubles).  b.mass is used through b.bc = 0.5 Cd A / m.
-template <bool DIAG>
+// SKIP = RB_FLAG_SKIP_NEGLIGIBLE_DRAG compiled in (a separate instantiation, so the default path
+// carries no extra compare / branch).
+template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
-                        double a[3], RhsOut *diag, double drag_skip_altitude = 1e300) {
+                        double a[3], RhsOut *diag) {
     const double x = r[0], y = r[1], z = r[2];
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
@@ -263,7 +267,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
     // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
     const double altitude = rn - KC(earth_r);
-    if (altitude <= drag_skip_altitude) {
+    if (!SKIP || altitude <= RB_NEGLIGIBLE_DRAG_ALTITUDE_) {
         // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
         const double ip = rb_rsqrt(p2);
         double gA, gB;
