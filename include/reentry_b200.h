@@ -65,6 +65,11 @@ typedef enum rb_traj_status {
                                    bc < 1e8 m^2/kg -- below one ulp of every other term -- so latitude, density and
                                    drag are not evaluated there.  Off by default; orbit ensembles run ~2.5x faster */
 #define RB_NEGLIGIBLE_DRAG_ALTITUDE 400000.0
+#define RB_FLAG_NO_OVERLAP 32u   /* do not split large ensembles (>= RB_OVERLAP_MIN_TRAJECTORIES) into two
+                                   partitions running on two streams (the second is library-owned; both are
+                                   ordered after prior work on `stream` and joined back before the call's last
+                                   kernel, so the caller still sees ONE stream) */
+#define RB_OVERLAP_MIN_TRAJECTORIES 600000
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */
 
@@ -160,7 +165,8 @@ typedef struct rb_stats {
     int64_t propagate_launches;  /* launches of the step kernel */
     int64_t steps_enqueued;      /* steps covered by those launches */
     int64_t last_polled_live;    /* last live count the host saw (-1 if never polled) */
-    double propagate_ms;         /* sum of step-kernel durations (RB_FLAG_PROFILE only, else 0) */
+    double propagate_ms;         /* device time of the step-kernel launch sequence, first launch to last
+                                    (RB_FLAG_PROFILE only, else 0) */
 } rb_stats;
 int32_t rb_ctx_stats(const rb_ctx *ctx, rb_stats *out);
 

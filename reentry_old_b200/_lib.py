@@ -16,6 +16,7 @@ RB_FLAG_EARLY_EXIT = 2
 RB_FLAG_NO_REFINE = 4
 RB_FLAG_PROFILE = 8
 RB_FLAG_SKIP_NEGLIGIBLE_DRAG = 16
+RB_FLAG_NO_OVERLAP = 32
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
 RB_DIAG_FIELDS = 23

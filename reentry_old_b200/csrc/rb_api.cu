@@ -40,10 +40,12 @@ struct rb_ctx {
     // workspace
     int32_t *d_live[2] = {nullptr, nullptr};
     int32_t *d_block_counts = nullptr;
-    int32_t *d_n_live = nullptr;  // [0] live count, [1] fresh count (scratch), [2] edge-sample counter
+    int32_t *d_n_live = nullptr;  // per partition q: [4q] live count, [4q+1] fresh count; [8] edge-sample counter
     int64_t ws_n = 0;
     int32_t *h_poll = nullptr;  // pinned ring
-    cudaEvent_t poll_ev[8] = {};
+    cudaEvent_t poll_ev[16] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr, span_ev[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream = nullptr;  // second partition
     bool events_ready = false;
     // host-path device buffers (grow-only)
     void *d_host_bufs[8] = {nullptr};
@@ -53,7 +55,6 @@ struct rb_ctx {
     double *h_table = nullptr;  // pinned staging for the table
     int64_t h_table_entries = 0;
     rb_stats stats = {0, 0, 0, -1, 0.0};
-    std::vector<cudaEvent_t> prof_events;
 };
 
 static int32_t cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what) {
@@ -95,9 +96,14 @@ int32_t rb_ctx_create(rb_ctx **out, int32_t device) {
     if (!ctx) return RB_ERR_NOMEM;
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n_live, 4 * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_poll, 8 * sizeof(int32_t), cudaHostAllocDefault);
-    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->poll_ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n_live, 12 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_poll, 16 * sizeof(int32_t), cudaHostAllocDefault);
+    for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->poll_ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->span_ev[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->span_ev[1]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         ctx->events_ready = true;
         e = cudaFuncSetAttribute(k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -129,7 +135,10 @@ int32_t rb_ctx_destroy(rb_ctx *ctx) {
     for (auto &b : ctx->d_host_bufs) cudaFree(b);
     if (ctx->events_ready)
         for (auto &ev : ctx->poll_ev) cudaEventDestroy(ev);
-    for (auto &ev : ctx->prof_events) cudaEventDestroy(ev);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+    for (auto &ev : ctx->span_ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
     delete ctx;
@@ -250,16 +259,35 @@ static int32_t ensure_workspace(rb_ctx *ctx, int64_t n, cudaStream_t stream) {
     ctx->ws_n = 0;
     CK(cudaMalloc(&ctx->d_live[0], (size_t)n * sizeof(int32_t)));
     CK(cudaMalloc(&ctx->d_live[1], (size_t)n * sizeof(int32_t)));
-    CK(cudaMalloc(&ctx->d_block_counts, (size_t)((n + COMPACT_BLOCK - 1) / COMPACT_BLOCK + 1) * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_block_counts, (size_t)((n + COMPACT_BLOCK - 1) / COMPACT_BLOCK + 8) * sizeof(int32_t)));
     ctx->ws_n = n;
     return RB_OK;
 }
 
 // Called after the launch that completed `steps_done` steps of the run has been enqueued.
 struct LaunchHook {
-    virtual void after_launch(int64_t steps_done, cudaStream_t stream) = 0;
+    virtual void after_launch(int64_t steps_done, const cudaStream_t *streams, int n_streams) = 0;
     virtual ~LaunchHook() {}
 };
+
+// One partition of the ensemble: its own live list window, counters and stream.  Two partitions on
+// two streams let the ragged tail of one partition's launch (last partial wave, retired lanes)
+// overlap with the body of the other's (+3.6 % on C2, profiles/r1_variant_sweep.txt).
+struct Part {
+    int64_t start = 0, count = 0, live_bound = 0;
+    int cur = 0;
+    bool finished = false;
+    cudaStream_t s = nullptr;
+    int32_t *n_live = nullptr;       // device [2]: live count, fresh count
+    int32_t *block_counts = nullptr; // device, this partition's slice
+    int32_t *h_poll = nullptr;       // pinned ring [8]
+    cudaEvent_t *poll_ev = nullptr;  // [8]
+};
+
+__global__ void k_set_counts(int32_t *a, int32_t va, int32_t *b, int32_t vb) {
+    a[0] = va; a[1] = va;
+    if (b) { b[0] = vb; b[1] = vb; }
+}
 
 static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, const rb_out *out, cudaStream_t stream,
                               LaunchHook *hook, int64_t *steps_done_out) {
@@ -284,89 +312,119 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     const bool early = (run->flags & RB_FLAG_EARLY_EXIT) != 0;
     const bool profile = (run->flags & RB_FLAG_PROFILE) != 0;
     const bool skip_drag = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) != 0;
-    size_t prof_used = 0;
-    auto prof_event = [&]() -> cudaEvent_t {
-        if (prof_used == ctx->prof_events.size()) {
-            cudaEvent_t ev = nullptr;
-            cudaEventCreate(&ev);
-            ctx->prof_events.push_back(ev);
-        }
-        return ctx->prof_events[prof_used++];
-    };
+
+    // partitions: two when each half still fills the machine several times over
+    const int n_parts = (n >= RB_OVERLAP_MIN_TRAJECTORIES && !(run->flags & RB_FLAG_NO_OVERLAP)) ? 2 : 1;
+    Part parts[2];
+    for (int q = 0; q < n_parts; ++q) {
+        Part &pt = parts[q];
+        pt.start = (q == 0) ? 0 : n / 2;
+        pt.count = (n_parts == 1) ? n : (q == 0 ? n / 2 : n - n / 2);
+        pt.live_bound = pt.count;
+        pt.s = (q == 0) ? stream : ctx->aux_stream;
+        pt.n_live = ctx->d_n_live + 4 * q;
+        pt.block_counts = ctx->d_block_counts + ((q == 0) ? 0 : (n / 2 + COMPACT_BLOCK - 1) / COMPACT_BLOCK + 1);
+        pt.h_poll = ctx->h_poll + 8 * q;
+        pt.poll_ev = ctx->poll_ev + 8 * q;
+    }
 
     InitParams ip{};
     ip.y0 = in->y0; ip.y0_traj_stride = in->y0_traj_stride; ip.y0_comp_stride = in->y0_comp_stride;
-    ip.state = out->final_state; ip.n = n; ip.live = ctx->d_live[0]; ip.n_live = ctx->d_n_live;
+    ip.state = out->final_state; ip.n = n; ip.live = ctx->d_live[0];
     ip.impact_step = out->impact_step; ip.impact_time = out->impact_time; ip.status = out->status;
     ip.samples = out->samples; ip.sample_stride = out->sample_stride; ip.field_stride = out->field_stride;
     k_init<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ip);
+    k_set_counts<<<1, 1, 0, stream>>>(parts[0].n_live, (int32_t)parts[0].count, n_parts > 1 ? parts[1].n_live : nullptr,
+                                     n_parts > 1 ? (int32_t)parts[1].count : 0);
+    CK(cudaMemsetAsync(ctx->d_n_live + 8, 0, sizeof(int32_t), stream));  // edge-sample counter of k_refine
     CK(cudaGetLastError());
-    ctx->stats.kernel_launches++;
+    ctx->stats.kernel_launches += 2;
+    if (profile) CK(cudaEventRecord(ctx->span_ev[0], stream));
+    if (n_parts > 1) {  // fork
+        CK(cudaEventRecord(ctx->fork_ev, stream));
+        CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
+    }
 
     StepParams sp{};
     sp.table = ctx->d_table; sp.out_stride = run->out_stride; sp.h = ctx->dt; sp.event_altitude = run->event_altitude;
     sp.state = out->final_state; sp.n = n;
     sp.cd = in->cd; sp.area = in->area; sp.mass = in->mass;
     sp.cd_s = in->cd_scalar; sp.area_s = in->area_scalar; sp.mass_s = in->mass_scalar;
-    sp.n_live = ctx->d_n_live;
     sp.samples = out->samples; sp.sample_stride = out->sample_stride; sp.field_stride = out->field_stride;
     sp.impact_step = out->impact_step; sp.status = out->status;
 
-    int cur = 0;               // live list in use
-    int64_t live_bound = n;    // host-side upper bound of the live count
     int64_t done = 0;
     int64_t launch_idx = 0;
     const size_t smem = propagate_smem_bytes<RB_BLOCK>();
     while (done < run->n_steps) {
-        if (early && launch_idx >= 2) {  // look at the live count published 2 launches ago
+        if (early && launch_idx >= 2) {  // look at the live counts published 2 launches ago (never blocks the GPU)
             const int slot = (int)((launch_idx - 2) & 7);
-            CK(cudaEventSynchronize(ctx->poll_ev[slot]));
-            const int32_t seen = ctx->h_poll[slot];
-            ctx->stats.last_polled_live = seen;
-            if (compact) live_bound = std::min<int64_t>(live_bound, seen);  // the list only shrinks when compacted
-            if (seen == 0) break;
+            int64_t seen_total = 0;
+            for (int q = 0; q < n_parts; ++q) {
+                Part &pt = parts[q];
+                if (pt.finished) continue;
+                CK(cudaEventSynchronize(pt.poll_ev[slot]));
+                const int32_t seen = pt.h_poll[slot];
+                if (compact) pt.live_bound = std::min<int64_t>(pt.live_bound, seen);  // the list only shrinks when compacted
+                if (seen == 0) pt.finished = true;
+                seen_total += seen;
+            }
+            ctx->stats.last_polled_live = seen_total;
+            if (seen_total == 0) break;
         }
         const int64_t steps = std::min<int64_t>(spl, run->n_steps - done);
         sp.table_step0 = run->first_step + done;
         sp.run_step0 = done;
         sp.n_launch_steps = (int)steps;
-        sp.live = ctx->d_live[cur];
-        const unsigned grid = (unsigned)((live_bound + RB_BLOCK - 1) / RB_BLOCK);
-        if (profile) CK(cudaEventRecord(prof_event(), stream));
-        if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, stream>>>(sp);
-        else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, stream>>>(sp);
-        CK(cudaGetLastError());
-        if (profile) CK(cudaEventRecord(prof_event(), stream));
-        ctx->stats.kernel_launches++;
-        ctx->stats.propagate_launches++;
-        ctx->stats.steps_enqueued += steps;
-        done += steps;
-        if ((compact || early) && done < run->n_steps) {
-            const unsigned cgrid = (unsigned)((live_bound + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
-            k_count_live<<<cgrid, COMPACT_BLOCK, 0, stream>>>(ctx->d_live[cur], ctx->d_n_live, out->status, ctx->d_block_counts);
-            k_scan_blocks<<<1, 1024, 0, stream>>>(ctx->d_block_counts, (int)cgrid, ctx->d_n_live + 1);
-            ctx->stats.kernel_launches += 2;
-            if (compact) {
-                k_scatter_live<<<cgrid, COMPACT_BLOCK, 0, stream>>>(ctx->d_live[cur], ctx->d_n_live, out->status,
-                                                                    ctx->d_block_counts, ctx->d_live[cur ^ 1]);
-                CK(cudaMemcpyAsync(ctx->d_n_live, ctx->d_n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-                ctx->stats.kernel_launches++;
-                cur ^= 1;
-            }
+        cudaStream_t active[2];
+        int n_active = 0;
+        for (int q = 0; q < n_parts; ++q) {
+            Part &pt = parts[q];
+            if (pt.finished) continue;
+            active[n_active++] = pt.s;
+            sp.live = ctx->d_live[pt.cur] + pt.start;
+            sp.n_live = pt.n_live;
+            const unsigned grid = (unsigned)((pt.live_bound + RB_BLOCK - 1) / RB_BLOCK);
+            if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
+            else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
             CK(cudaGetLastError());
-            if (early) {
-                const int slot = (int)(launch_idx & 7);
-                CK(cudaMemcpyAsync(&ctx->h_poll[slot], ctx->d_n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-                CK(cudaEventRecord(ctx->poll_ev[slot], stream));
+            ctx->stats.kernel_launches++;
+            ctx->stats.propagate_launches++;
+            if ((compact || early) && done + steps < run->n_steps) {
+                const unsigned cgrid = (unsigned)((pt.live_bound + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
+                const int32_t *lin = ctx->d_live[pt.cur] + pt.start;
+                k_count_live<<<cgrid, COMPACT_BLOCK, 0, pt.s>>>(lin, pt.n_live, out->status, pt.block_counts);
+                k_scan_blocks<<<1, 1024, 0, pt.s>>>(pt.block_counts, (int)cgrid, pt.n_live + 1);
+                ctx->stats.kernel_launches += 2;
+                if (compact) {
+                    k_scatter_live<<<cgrid, COMPACT_BLOCK, 0, pt.s>>>(lin, pt.n_live, out->status, pt.block_counts,
+                                                                     ctx->d_live[pt.cur ^ 1] + pt.start);
+                    CK(cudaMemcpyAsync(pt.n_live, pt.n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, pt.s));
+                    ctx->stats.kernel_launches++;
+                    pt.cur ^= 1;
+                }
+                CK(cudaGetLastError());
+                if (early) {
+                    const int slot = (int)(launch_idx & 7);
+                    CK(cudaMemcpyAsync(&pt.h_poll[slot], pt.n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, pt.s));
+                    CK(cudaEventRecord(pt.poll_ev[slot], pt.s));
+                }
             }
         }
-        if (hook) hook->after_launch(done, stream);
+        ctx->stats.steps_enqueued += steps;
+        done += steps;
+        if (hook) hook->after_launch(done, active, n_active);
         ++launch_idx;
     }
+    if (n_parts > 1) {  // join
+        CK(cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+        CK(cudaStreamWaitEvent(stream, ctx->join_ev, 0));
+    }
+    if (profile) CK(cudaEventRecord(ctx->span_ev[1], stream));
 
     RefineParams rp{};
     rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.event_altitude = run->event_altitude;
-    rp.skip_drag = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) ? 1 : 0;
+    rp.skip_drag = skip_drag ? 1 : 0;
     rp.state = out->final_state; rp.n = n;
     rp.cd = in->cd; rp.area = in->area; rp.mass = in->mass;
     rp.cd_s = in->cd_scalar; rp.area_s = in->area_scalar; rp.mass_s = in->mass_scalar;
@@ -375,21 +433,16 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     rp.samples = out->samples; rp.sample_stride = out->sample_stride; rp.field_stride = out->field_stride;
     rp.out_stride = run->out_stride; rp.run_first_step = run->first_step; rp.run_n_steps = run->n_steps;
     rp.refine = (run->flags & RB_FLAG_NO_REFINE) ? 0 : 1;
-    rp.edge_count = ctx->d_n_live + 2;
-    CK(cudaMemsetAsync(ctx->d_n_live + 2, 0, sizeof(int32_t), stream));
+    rp.edge_count = ctx->d_n_live + 8;
     k_refine<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(rp);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
     if (steps_done_out) *steps_done_out = done;
     if (profile) {
         CK(cudaStreamSynchronize(stream));
-        double ms = 0.0;
-        for (size_t k = 0; k + 1 < prof_used; k += 2) {
-            float t = 0.f;
-            CK(cudaEventElapsedTime(&t, ctx->prof_events[k], ctx->prof_events[k + 1]));
-            ms += t;
-        }
-        ctx->stats.propagate_ms = ms;
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, ctx->span_ev[0], ctx->span_ev[1]));
+        ctx->stats.propagate_ms = t;  // span of the step-kernel launch sequence (compaction included, < 0.5 %)
     }
     return RB_OK;
 }
@@ -430,14 +483,17 @@ struct SampleDownloader : LaunchHook {
     double *h_samples;
     int64_t n, out_stride, rows_copied = 0;
     cudaStream_t copy_stream;
-    cudaEvent_t ev;
+    cudaEvent_t ev[2];
     cudaError_t err = cudaSuccess;
-    void after_launch(int64_t steps_done, cudaStream_t stream) override {
-        // rows k <= steps_done/out_stride are final once this launch has finished
+    void after_launch(int64_t steps_done, const cudaStream_t *streams, int n_streams) override {
+        // rows k <= steps_done/out_stride are final once this launch has finished on every partition stream
         const int64_t rows_ready = steps_done / out_stride + 1;
         if (rows_ready <= rows_copied) return;
-        cudaError_t e = cudaEventRecord(ev, stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, ev, 0);
+        cudaError_t e = cudaSuccess;
+        for (int q = 0; q < n_streams && e == cudaSuccess; ++q) {
+            e = cudaEventRecord(ev[q], streams[q]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, ev[q], 0);
+        }
         const size_t row = (size_t)RB_SAMPLE_FIELDS * n * sizeof(double);
         if (e == cudaSuccess)
             e = cudaMemcpyAsync((char *)h_samples + rows_copied * row, (const char *)d_samples + rows_copied * row,
@@ -509,8 +565,9 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     SampleDownloader dl;
     dl.ctx = ctx; dl.d_samples = (const double *)d_samples; dl.h_samples = samples; dl.n = n;
     dl.out_stride = run->out_stride; dl.copy_stream = ctx->copy_stream;
-    cudaEvent_t ev = nullptr;
-    if (samples) { CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); dl.ev = ev; }
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (samples)
+        for (int q = 0; q < 2; ++q) { CK(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming)); dl.ev[q] = ev[q]; }
     rb_run r2 = *run;
     r2.flags |= RB_FLAG_EARLY_EXIT;
     int64_t steps_done = 0;
@@ -525,9 +582,9 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess && n_samples) e = cudaMemcpyAsync(n_samples, d_ns, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
         int32_t edge = 0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&edge, ctx->d_n_live + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&edge, ctx->d_n_live + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess && samples) {
-            dl.after_launch(steps_done, cs);  // rows not yet sent
+            dl.after_launch(steps_done, &cs, 1);  // rows not yet sent (k_refine has joined the partitions)
             if (dl.err != cudaSuccess) e = dl.err;
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
@@ -540,7 +597,8 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "rb_propagate_host download");
     }
-    if (ev) cudaEventDestroy(ev);
+    for (int q = 0; q < 2; ++q)
+        if (ev[q]) cudaEventDestroy(ev[q]);
     if (n_samples_used) *n_samples_used = samples ? dl.rows_copied : 0;
     return rc;
 }

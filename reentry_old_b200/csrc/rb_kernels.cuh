@@ -140,7 +140,6 @@ struct InitParams {
     double *state;
     int64_t n;
     int32_t *live;
-    int32_t *n_live;
     int32_t *impact_step;
     double *impact_time;
     uint8_t *status;
@@ -150,7 +149,6 @@ struct InitParams {
 
 __global__ void k_init(const InitParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *p.n_live = (int32_t)p.n;
     if (i >= p.n) return;
     double y[6];
 #pragma unroll

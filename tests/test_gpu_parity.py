@@ -204,6 +204,27 @@ def test_results_do_not_depend_on_launch_structure(Model, torch):
         assert torch.equal(r.n_samples, base.n_samples), kw
 
 
+def test_two_partition_overlap_is_invisible(Model, torch):
+    """Ensembles >= 600k trajectories run as two partitions on two streams; results are bit-identical
+    to the single-stream run and the caller's stream ordering holds (results complete after its sync)."""
+    from reentry_old_b200.configs import reentry_dispersion_params
+
+    n = 640_001   # odd: unequal halves
+    m = Model(Cd=1.3, A=14.0, m=5000.0)
+    y0 = m.get_initial_states(*reentry_dispersion_params(n, seed=21).T)
+    a = m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=128, overlap=True)
+    b = m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=128, overlap=False)
+    torch.cuda.synchronize()
+    assert a.stats["propagate_launches"] > b.stats["propagate_launches"]
+    assert torch.equal(torch.nan_to_num(a.samples, nan=-1.0), torch.nan_to_num(b.samples, nan=-1.0))
+    for k in ("final_state", "impact_step", "status", "n_samples"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert torch.equal(torch.nan_to_num(a.impact_time), torch.nan_to_num(b.impact_time))
+    assert int((a.status == 1).sum()) == n
+    c = m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=128, overlap=True, early_exit=False, compact=False)
+    assert torch.equal(c.impact_step, a.impact_step) and torch.equal(c.final_state, a.final_state)
+
+
 def test_soa_input_and_per_trajectory_bodies(Model, torch, oracle):
     rng = np.random.default_rng(8)
     n = 300
