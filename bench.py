@@ -316,10 +316,12 @@ def main():
             el, e2e_total = float(a[0]), float(b[1])
         else:
             e2e_total = float(e2e_steps)
-        d2h = (used.value * 8 * n * 8 if samples_h is not None else 0) + n * (48 + 4 + 8 + 1 + 4)
+        # pinned sample buffer -> the kernel stores the valid samples straight into host memory (zero-copy)
+        d2h = (int(ns_h.to(torch.int64).sum()) * SAMPLE_BYTES if samples_h is not None else 0) + n * (48 + 4 + 8 + 1 + 4)
         e2e = {"value": e2e_total * K / el, "unit": UNIT, "h2d_bytes_per_step": n * 48 + (5 * w.n_steps + 1) * 128,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * el / K,
-               "api": "rb_propagate_host (C ABI, pinned host buffers; time table built on the host inside the call)"}
+               "api": "rb_propagate_host (C ABI, pinned host buffers; time table built on the host inside the call; "
+                      "samples stored by the kernel directly into the pinned host buffer over PCIe)"}
         del samples_h
 
     cpu = None

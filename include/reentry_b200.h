@@ -70,6 +70,7 @@ typedef enum rb_traj_status {
                                    ordered after prior work on `stream` and joined back before the call's last
                                    kernel, so the caller still sees ONE stream) */
 #define RB_OVERLAP_MIN_TRAJECTORIES 600000
+#define RB_FLAG_STAGED_SAMPLES 64u /* rb_propagate_host: never write samples directly into pinned host memory */
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */
 
@@ -211,7 +212,11 @@ int32_t rb_impact_points(rb_ctx *ctx, int64_t n, const double *final_state, cons
 /* ---- host-buffer convenience (the end-to-end call of a ctypes / cgo style binding) ----
  * Everything is HOST memory (pinned memory from rb_host_alloc makes the copies asynchronous):
  * y0 [n][6]; cd/area/mass [n] or NULL; samples [n_out][8][n] or NULL; final_state [n][6].
- * Builds the time table, uploads, propagates, downloads, synchronises. */
+ * Builds the time table, uploads, propagates, downloads, synchronises.
+ * samples: only rows < *n_samples_used are touched.  If the buffer is pinned (rb_host_alloc,
+ * cudaHostAlloc, cudaHostRegister) the step kernel stores the samples straight into it (zero-copy)
+ * and entries of trajectory i at rows >= n_samples[i] keep what the caller had there; a pageable
+ * buffer is filled through a device staging buffer and those entries are NaN. */
 int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double *cd, const double *area,
                           const double *mass, double cd_scalar, double area_scalar, double mass_scalar,
                           double epoch_jd, double gmst0, double t0, double dt, const rb_run *run,

@@ -541,10 +541,23 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     if ((rc = host_buf(ctx, 5, (size_t)n, &d_status))) return rc;
     if ((rc = host_buf(ctx, 6, (size_t)n * 4, &d_ns))) return rc;
     const size_t row = (size_t)RB_SAMPLE_FIELDS * n * sizeof(double);
+    // Pinned (cudaHostAlloc / cudaHostRegister) sample buffers are written DIRECTLY by the step kernel over
+    // PCIe (zero-copy streaming stores): the download is fused into the producing kernel, only valid samples
+    // cross the link, and nothing is left to copy when the last launch ends.  Pageable buffers go through
+    // a NaN-filled device buffer and chunked cudaMemcpyAsync.
+    bool zero_copy = false;
     if (samples) {
-        if ((rc = host_buf(ctx, 7, (size_t)n_out * row, &d_samples))) return rc;
-        const int64_t cnt = n_out * RB_SAMPLE_FIELDS * n;
-        k_fill_nan<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>((double *)d_samples, cnt);
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, samples) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer &&
+            !(run->flags & RB_FLAG_STAGED_SAMPLES)) {
+            zero_copy = true;
+            d_samples = attr.devicePointer;
+        } else {
+            (void)cudaGetLastError();
+            if ((rc = host_buf(ctx, 7, (size_t)n_out * row, &d_samples))) return rc;
+            const int64_t cnt = n_out * RB_SAMPLE_FIELDS * n;
+            k_fill_nan<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>((double *)d_samples, cnt);
+        }
     }
     CK(cudaMemcpyAsync(d_y0, y0, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, cs));
     double *d_cd = nullptr, *d_area = nullptr, *d_mass = nullptr;
@@ -566,12 +579,13 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     dl.ctx = ctx; dl.d_samples = (const double *)d_samples; dl.h_samples = samples; dl.n = n;
     dl.out_stride = run->out_stride; dl.copy_stream = ctx->copy_stream;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    if (samples)
+    const bool staged = samples && !zero_copy;
+    if (staged)
         for (int q = 0; q < 2; ++q) { CK(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming)); dl.ev[q] = ev[q]; }
     rb_run r2 = *run;
     r2.flags |= RB_FLAG_EARLY_EXIT;
     int64_t steps_done = 0;
-    rc = propagate_impl(ctx, &in, &r2, &out, cs, samples ? &dl : nullptr, &steps_done);
+    rc = propagate_impl(ctx, &in, &r2, &out, cs, staged ? &dl : nullptr, &steps_done);
     if (rc == RB_OK) {
         double *d_aos = (double *)d_state + 6 * n;
         k_soa_to_aos6<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>((const double *)d_state, d_aos, n);
@@ -583,12 +597,12 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         if (e == cudaSuccess && n_samples) e = cudaMemcpyAsync(n_samples, d_ns, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
         int32_t edge = 0;
         if (e == cudaSuccess) e = cudaMemcpyAsync(&edge, ctx->d_n_live + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
-        if (e == cudaSuccess && samples) {
+        if (e == cudaSuccess && staged) {
             dl.after_launch(steps_done, &cs, 1);  // rows not yet sent (k_refine has joined the partitions)
             if (dl.err != cudaSuccess) e = dl.err;
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
-        if (e == cudaSuccess && samples && edge > 0) {
+        if (e == cudaSuccess && staged && edge > 0) {
             // a grid sample coincided with an event time and was added by k_refine after its row had
             // been sent (measure-zero case): send the rows again
             e = cudaMemcpyAsync(samples, d_samples, (size_t)dl.rows_copied * row, cudaMemcpyDeviceToHost, cs);
@@ -599,7 +613,7 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     }
     for (int q = 0; q < 2; ++q)
         if (ev[q]) cudaEventDestroy(ev[q]);
-    if (n_samples_used) *n_samples_used = samples ? dl.rows_copied : 0;
+    if (n_samples_used) *n_samples_used = !samples ? 0 : (staged ? dl.rows_copied : steps_done / run->out_stride + 1);
     return rc;
 }
 

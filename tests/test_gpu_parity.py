@@ -306,6 +306,44 @@ def test_propagate_host_matches_device_path(Model, torch):
     assert np.array_equal(np.nan_to_num(samples[:k], nan=-1.0), np.nan_to_num(r.samples[:k].cpu().numpy(), nan=-1.0))
 
 
+def test_propagate_host_zero_copy_samples(Model, torch):
+    """Pinned sample buffers are written directly by the kernel (no staging copy): valid entries equal the
+    device path bit for bit, entries after each trajectory's event keep the caller's fill value."""
+    import ctypes as C
+
+    from reentry_old_b200 import _lib as L
+    from reentry_old_b200.configs import reentry_dispersion_params
+    from reentry_old_b200.model import DeviceContext
+
+    n, n_steps, stride = 20_000, 2048, 16
+    m = Model(Cd=1.3, A=14.0, m=5000.0)
+    y0 = m.get_initial_states(*reentry_dispersion_params(n, seed=12).T)
+    r = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=stride)
+    ctx = DeviceContext.get()
+    n_out = n_steps // stride + 1
+    y0h = y0.cpu().pin_memory()
+    fs = torch.empty((n, 6), dtype=torch.float64).pin_memory(); ist = torch.empty(n, dtype=torch.int32).pin_memory()
+    it = torch.empty(n, dtype=torch.float64).pin_memory(); st = torch.empty(n, dtype=torch.uint8).pin_memory()
+    ns = torch.empty(n, dtype=torch.int32).pin_memory(); used = C.c_int64(0)
+    for flags in (L.RB_FLAG_COMPACT, L.RB_FLAG_COMPACT | L.RB_FLAG_STAGED_SAMPLES):
+        samples = torch.full((n_out, 8, n), -7.0, dtype=torch.float64).pin_memory()
+        run = L.RbRun(first_step=0, n_steps=n_steps, out_stride=stride, steps_per_launch=32, event_altitude=1000.0, flags=flags)
+        rc = ctx.lib.rb_propagate_host(ctx.handle, n, y0h.data_ptr(), None, None, None, 1.3, 14.0, 5000.0, m.epoch, m.gmst0, 0.0,
+                                       0.5, C.byref(run), samples.data_ptr(), n_out, fs.data_ptr(), ist.data_ptr(), it.data_ptr(),
+                                       st.data_ptr(), ns.data_ptr(), C.byref(used))
+        assert rc == 0, ctx.lib.rb_ctx_last_error(ctx.handle)
+        ctx.table_key = None
+        k = used.value
+        ref = r.samples[:k].cpu()
+        valid = ~torch.isnan(ref)
+        assert torch.equal(samples[:k][valid], ref[valid])
+        fill = -7.0 if flags == L.RB_FLAG_COMPACT else float("nan")           # zero-copy leaves, staging NaN-fills
+        rest = samples[:k][~valid]
+        assert bool(torch.isnan(rest).all()) if fill != fill else bool((rest == fill).all())
+        assert bool((samples[k:] == -7.0).all())
+        assert torch.equal(ns, r.n_samples.cpu()) and torch.equal(ist, r.impact_step.cpu())
+
+
 def test_error_codes(Model, torch):
     import ctypes as C
 
