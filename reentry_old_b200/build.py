@@ -28,6 +28,7 @@ def nvcc_path() -> str:
 
 def command(extra=(), out=LIB):
     return [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+            "-fmad=false",  # every fused multiply-add is written out as fma(): identical arithmetic in every kernel instantiation
             "-Xcompiler", "-fPIC,-fopenmp,-O2", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
             *extra, "-o", out, *SOURCES]
 

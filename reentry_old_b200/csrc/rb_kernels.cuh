@@ -26,6 +26,10 @@ namespace rb {
 #ifndef RB_TILE_STEPS
 #define RB_TILE_STEPS 8
 #endif
+#ifndef RB_TILE_BUFFERS
+#define RB_TILE_BUFFERS 2
+#endif
+constexpr int TILE_BUFFERS = RB_TILE_BUFFERS;  // 1 = single buffer (TMA latency exposed once per tile), 2 = double
 constexpr int TILE_STEPS = RB_TILE_STEPS;                                      // steps per time-table tile
 constexpr int TILE_ENTRIES = RB_STAGES_PER_STEP * TILE_STEPS + 1;  // 41 entries
 constexpr int TILE_DOUBLES = TILE_ENTRIES * ENTRY_DOUBLES;          // 656 doubles = 5248 B
@@ -173,14 +177,14 @@ __global__ void k_init(const InitParams p) {
 // Shared memory: [2 x tile][Ka slots: 7 x 3 x BLOCK doubles][2 mbarriers]
 template <int BLOCK>
 constexpr size_t propagate_smem_bytes() {
-    return sizeof(double) * (2 * TILE_DOUBLES + K_SLOTS * K_ROWS * BLOCK) + 2 * sizeof(uint64_t);
+    return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + K_SLOTS * K_ROWS * BLOCK) + 2 * sizeof(uint64_t);
 }
 
 template <int BLOCK, int MIN_BLOCKS, bool SKIP>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
-    double *Ks = tiles + 2 * TILE_DOUBLES;
+    double *Ks = tiles + TILE_BUFFERS * TILE_DOUBLES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(Ks + K_SLOTS * K_ROWS * BLOCK);
 
     const int n_live = *p.n_live;
@@ -194,9 +198,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     auto issue_tile = [&](int t) {  // thread 0 only
         const uint32_t bytes = (uint32_t)((RB_STAGES_PER_STEP * tile_steps_of(t) + 1) * ENTRY_DOUBLES * sizeof(double));
         const double *src = p.table + (RB_STAGES_PER_STEP * (p.table_step0 + (int64_t)t * TILE_STEPS)) * ENTRY_DOUBLES;
-        uint64_t *bar = &bars[t & 1];
+        uint64_t *bar = &bars[t % TILE_BUFFERS];
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(tiles + (t & 1) * TILE_DOUBLES, src, bytes, bar);
+        bulk_g2s(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES, src, bytes, bar);
     };
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         fence_barrier_init();
         fence_proxy_async();
         issue_tile(0);
-        if (n_tiles > 1) issue_tile(1);
+        if (TILE_BUFFERS > 1 && n_tiles > 1) issue_tile(1);
     }
 
     // per-trajectory state
@@ -235,8 +239,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     const double h = p.h, hh = p.h * p.h;
 
     for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
-        const double *tile = tiles + (t & 1) * TILE_DOUBLES;
+        mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
+        const double *tile = tiles + (t % TILE_BUFFERS) * TILE_DOUBLES;
         const int ts = tile_steps_of(t);
         // stage loop flattened so that the acceleration code exists ONCE in the kernel:
         // s = 0 only for the very first evaluation of the launch (Ka_0 = a(t_n, y_n)).
@@ -266,10 +270,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 if (s == 6) {
                     // step complete: ys = y_{n+1}
                     const double r2n = fma(ys[2], ys[2], fma(ys[0], ys[0], ys[1] * ys[1]));
-                    const double rn_new = r2n * rb_rsqrt(r2n);
-                    const double g_new = rn_new - KC(earth_r) - p.event_altitude;
+                    const double alt_new = fma(r2n, rb_rsqrt(r2n), -KC(earth_r));   // |r| - R
+                    const double g_new = alt_new - p.event_altitude;
                     const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
-                    const bool finite = fabs(ys[0] + ys[1] + ys[2] + ys[3] + ys[4] + ys[5]) <= DBL_MAX;
+                    // non-finite detection on the exponent bits of |r|^2 (a NaN/Inf velocity reaches r one step
+                    // later; the FP64 pipe is the bottleneck, integer compares are free)
+                    const bool finite = (__double2hiint(r2n) & 0x7ff00000) != 0x7ff00000;
                     if (!finite) {
                         alive = false;
                         p.status[tid] = RB_TRAJ_NONFINITE;
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                             double *sp = p.samples + next_k * p.sample_stride + tid;
 #pragma unroll
                             for (int c = 0; c < 6; ++c) st_stream(sp + c * p.field_stride, ys[c]);
-                            st_stream(sp + 6 * p.field_stride, rn_new - KC(earth_r));
+                            st_stream(sp + 6 * p.field_stride, alt_new);
                             const double v2 = fma(ys[5], ys[5], fma(ys[3], ys[3], ys[4] * ys[4]));
                             st_stream(sp + 7 * p.field_stride, sqrt(v2));
                         }
@@ -300,14 +306,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 if (--to_sample == 0) { to_sample = (int)p.out_stride; ++next_k; }
                 // warp-ballot retirement: a warp with no live lane leaves (warp 0 stays while
                 // tiles remain to be issued)
-                if (!__any_sync(0xffffffffu, alive) && (threadIdx.x >= 32 || t + 2 >= n_tiles)) goto done;
+                if (!__any_sync(0xffffffffu, alive) && (threadIdx.x >= 32 || t + TILE_BUFFERS >= n_tiles)) goto done;
             } else {
                 ++s;
             }
         }
-        if (t + 2 < n_tiles) {
-            __syncthreads();  // everyone is done reading buffer (t & 1)
-            if (threadIdx.x == 0) issue_tile(t + 2);
+        if (t + TILE_BUFFERS < n_tiles) {
+            __syncthreads();  // everyone is done reading this tile's buffer
+            if (threadIdx.x == 0) issue_tile(t + TILE_BUFFERS);
         }
     }
 done:

@@ -33,7 +33,7 @@ enum : int {
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
     double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r, tan_tol, rad2deg, latc;
-    double sig_ks, sig_x0, blend_alt, inv_rgas_dummy, rgas, top_h, top_T, top_P, top_k;
+    double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
     double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
@@ -56,7 +56,7 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
      RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
      1.0 - RB_EARTH_E2 * RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 180.0 / RB_PI,           \
      RB_LAT_FACTOR_COEF / 90.0, RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
-     RB_SOLAR_BLEND_ALT, 0.0, RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
+     RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
      RB_L8_(rb_powk_), RB_L8_(rb_invbt_)}
@@ -191,33 +191,29 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
     if (altitude < KC(blend_alt)) {
-        const double normalized = rb_rcp(1.0 + rb_exp(-KC(sig_ks) * (altitude - KC(sig_x0))));
+        double ep, es;
+        rb_exp_parts(-KC(sig_ks) * (altitude - KC(sig_x0)), ep, es);
+        const double normalized = rb_rcp(fma(ep, es, 1.0));   // 1 / (1 + e^(-k (x - x0)))
         factor = fma(factor - 1.0, normalized, 1.0);
     }
     const double latitude_factor = fma(KC(latc), abs_latitude_deg, 1.0);
-    double P, T;
     if (altitude >= KC(top_h)) {  // top layer (i == 7): isothermal + the extra scale-height tail
-        T = KC(top_T);
-        P = KC(top_P) * rb_exp((altitude - KC(top_h)) * KC(top_k));
-    } else {
-        // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
-        int i = (altitude >= KC(bp[4])) ? 4 : 0;
-        i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
-        i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
-        const double dh = altitude - KC(bp[i]);
-        const double L = KC(gr[i]);
-        T = fma(L, dh, KC(bt[i]));
-        if (L == 0.0) P = KC(bpz[i]) * rb_exp(dh * KC(iso_k[i]));
-        else P = KC(bpz[i]) * rb_pow_near1(T * KC(inv_bt[i]), KC(pow_k[i]));
+        T_out = KC(top_T);        // P7 / (R_GAS T7) is a constant of the layer
+        return (KC(top_rho0) * rb_exp((altitude - KC(top_h)) * KC(top_k))) * (latitude_factor * factor);
     }
+    // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
+    int i = (altitude >= KC(bp[4])) ? 4 : 0;
+    i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
+    i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
+    const double dh = altitude - KC(bp[i]);
+    const double L = KC(gr[i]);
+    const double T = fma(L, dh, KC(bt[i]));
+    double P;
+    if (L == 0.0) P = KC(bpz[i]) * rb_exp(dh * KC(iso_k[i]));
+    else P = KC(bpz[i]) * rb_pow_near1(T * KC(inv_bt[i]), KC(pow_k[i]));
     T_out = T;
     return P * latitude_factor * rb_rcp(KC(rgas) * T) * factor;
 }
-
-// Full acceleration of SpacecraftModel.equations_of_motion (spacecraft_model.py:437-470).
-// e: time-table entry (16 doubles).  b.mass is used through b.bc = 0.5 Cd A / m.
-// SKIP = RB_FLAG_SKIP_NEGLIGIBLE_DRAG compiled in (a separate instantiation, so the default path
-// carries no extra compare / branch).
 template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
                         double a[3], RhsOut *diag) {
@@ -225,23 +221,24 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
     const double ir = rb_rsqrt(r2);                   // 1/|r|
-    const double rn = r2 * ir;                        // |r|  (euclidean_norm, :67-69, :439)
     const double ir2 = ir * ir, ir3 = ir2 * ir;
     // ground velocity (coordinate_converter.py:29-48, :447) and v_rel = v_ground - omega x r_ecef (:448);
     // rotating omega x r_ecef back is omega x r_eci, so v_rel is formed in ECI and |v_rel| is frame free
     const double wx = fma(KC(omega), y, v[0]), wy = fma(-KC(omega), x, v[1]), wz = v[2];
-    // point-mass gravity, :451 : -mu r / |r|^3
+    // point-mass gravity, :451 : -mu r / |r|^3, and J2, :377-388 : f = 1.5 mu J2 R^2 / r^5 ;
+    // a = f r (5 z^2/r^2 - {1,1,3}).  Both are (scalar) * r: the scalars are summed first.
     const double gk = KC(neg_mu) * ir3;
-    double ax = gk * x, ay = gk * y, az = gk * z;
-    if (DIAG) { diag->a_grav[0] = ax; diag->a_grav[1] = ay; diag->a_grav[2] = az; }
-    // J2, :377-388 : f = 1.5 mu J2 R^2 / r^5 ; a = f r (5 z^2/r^2 - {1,1,3})
-    {
-        const double f = KC(j2f) * (ir3 * ir2);
-        const double q = 5.0 * (z * z) * ir2;
-        const double fxy = (q - 1.0) * f, fz = (q - 3.0) * f;
-        const double jx = fxy * x, jy = fxy * y, jz = fz * z;
-        ax += jx; ay += jy; az += jz;
-        if (DIAG) { diag->a_j2[0] = jx; diag->a_j2[1] = jy; diag->a_j2[2] = jz; }
+    const double f = KC(j2f) * (ir3 * ir2);
+    const double q = (5.0 * ir2) * (z * z);
+    const double fxy = fma(q, f, -f), fz = fma(q, f, -3.0 * f);
+    double ax, ay, az;
+    if (DIAG) {
+        diag->a_grav[0] = gk * x; diag->a_grav[1] = gk * y; diag->a_grav[2] = gk * z;
+        diag->a_j2[0] = fxy * x; diag->a_j2[1] = fxy * y; diag->a_j2[2] = fz * z;
+        ax = diag->a_grav[0] + diag->a_j2[0]; ay = diag->a_grav[1] + diag->a_j2[1]; az = diag->a_grav[2] + diag->a_j2[2];
+    } else {
+        const double kxy = gk + fxy;
+        ax = kxy * x; ay = kxy * y; az = (gk + fz) * z;
     }
     // third bodies as a lambda: evaluated inside the drag block (fills the latency of its serial tail)
     // or on their own when the drag block is skipped
@@ -266,7 +263,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     };
     // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
     // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
-    const double altitude = rn - KC(earth_r);
+    const double altitude = fma(r2, ir, -KC(earth_r));   // |r| - R with |r| = r2 / sqrt(r2)  (:458)
     if (!SKIP || altitude <= RB_NEGLIGIBLE_DRAG_ALTITUDE_) {
         // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
         const double ip = rb_rsqrt(p2);
@@ -279,10 +276,12 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
         const double vn = w2 * rb_rsqrt(w2);
         const double kd = -(rho * b.bc) * vn;
-        const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;
-        ax += ddx; ay += ddy; az += ddz;
         if (DIAG) {
+            const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;
             diag->a_drag[0] = ddx; diag->a_drag[1] = ddy; diag->a_drag[2] = ddz;
+        }
+        ax = fma(kd, wx, ax); ay = fma(kd, wy, ay); az = fma(kd, wz, az);
+        if (DIAG) {
             diag->altitude = altitude; diag->latitude_deg = lat_deg; diag->rho = rho; diag->T = T; diag->v_rel_norm = vn;
         }
     } else {
@@ -299,7 +298,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
 // event function of run_simulation.altitude_event (spacecraft_model.py:496-501)
 RB_HD double event_g(const double r[3], double event_altitude) {
     const double r2 = fma(r[2], r[2], fma(r[0], r[0], r[1] * r[1]));
-    return r2 * rb_rsqrt(r2) - KC(earth_r) - event_altitude;
+    return fma(r2, rb_rsqrt(r2), -KC(earth_r)) - event_altitude;
 }
 
 // ---- Dormand-Prince tableau (scipy rk.py:541-565), row 6 of A = B (FSAL) ----

@@ -16,6 +16,7 @@ from reentry_old_b200.model import DeviceContext
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+spl = int(os.environ.get("RB_SPL", "0"))
 m = SpacecraftModel(Cd=1.3, A=14.0, m=5000.0)
 p = reentry_dispersion_params(n, 1234)
 y0 = m.get_initial_states(*p.T)
@@ -25,7 +26,7 @@ for stride, store in ((16, True), (2048, False)):
     for rep in range(reps):
         torch.cuda.synchronize()
         t = time.perf_counter()
-        r = m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=stride, store_samples=store, profile=True)
+        r = m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=stride, store_samples=store, profile=True, steps_per_launch=spl)
         torch.cuda.synchronize()
         el = time.perf_counter() - t
         steps = int(r.impact_step.clamp(min=0).sum())
