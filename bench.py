@@ -298,7 +298,8 @@ def main():
         ns_h = torch.empty(n, dtype=torch.int32).pin_memory()
         used = C.c_int64(0)
         run = L.RbRun(first_step=0, n_steps=w.n_steps, out_stride=w.out_stride, steps_per_launch=w.steps_per_launch,
-                      event_altitude=1000.0, flags=L.RB_FLAG_COMPACT)
+                      event_altitude=1000.0,
+                      flags=L.RB_FLAG_COMPACT | (L.RB_FLAG_STAGED_SAMPLES if os.environ.get("RB_E2E_STAGED") else 0))
 
         def host_pass():
             rc = lib.rb_propagate_host(ctx.handle, n, y0_h.data_ptr(), None, None, None, float(w.Cd), float(w.A),
