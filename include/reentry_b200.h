@@ -70,6 +70,8 @@ typedef enum rb_traj_status {
                                    ordered after prior work on `stream` and joined back before the call's last
                                    kernel, so the caller still sees ONE stream) */
 #define RB_OVERLAP_MIN_TRAJECTORIES 600000
+#define RB_FLAG_PAIRWISE_KERNEL 128u /* use the two-trajectories-per-thread step kernel while a partition has >= 200k
+                                   live trajectories (bit-identical results; off by default: not faster on B200) */
 #define RB_FLAG_STAGED_SAMPLES 64u /* rb_propagate_host: never write samples directly into pinned host memory */
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */

@@ -295,6 +295,110 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     a[0] = ax; a[1] = ay; a[2] = az;
 }
 
+// ---- two trajectories per thread -----------------------------------------------------------
+// The B200 FP64 pipe issues one warp-instruction per 2 cycles only when consecutive FP64
+// instructions of the SAME warp are independent; dependent single-chain code saturates at one per
+// 3 cycles however many warps are resident (profiles/r1_variant_sweep.txt, tools/ubench).  The RHS
+// is a long dependent chain, so the step kernel evaluates it for TWO trajectories per thread with
+// the statements of the pair adjacent: every operation below is the scalar acceleration<false>()
+// operation for operation (bit-identical results), written over [2] arrays with unrolled loops so
+// that the pair shares basic blocks; the data-dependent geodetic loop runs until both have
+// converged (finished members are frozen by selects) and the uncommon atmosphere branches fall back
+// to the scalar density().
+#define RB_PAIR _Pragma("unroll") for (int c = 0; c < 2; ++c)
+RB_HD void acceleration2(const double *__restrict__ e, const double r[2][3], const double v[2][3], const Body b[2],
+                         double a[2][3]) {
+    double x[2], y[2], z[2], p2[2], r2[2], ir[2], wx[2], wy[2], wz[2], ax[2], ay[2], az[2], altitude[2];
+    RB_PAIR {
+        x[c] = r[c][0]; y[c] = r[c][1]; z[c] = r[c][2];
+        p2[c] = fma(x[c], x[c], y[c] * y[c]);
+        r2[c] = fma(z[c], z[c], p2[c]);
+        ir[c] = rb_rsqrt(r2[c]);
+    }
+    RB_PAIR {
+        const double ir2 = ir[c] * ir[c], ir3 = ir2 * ir[c];
+        wx[c] = fma(KC(omega), y[c], v[c][0]); wy[c] = fma(-KC(omega), x[c], v[c][1]); wz[c] = v[c][2];
+        const double gk = KC(neg_mu) * ir3;
+        const double f = KC(j2f) * (ir3 * ir2);
+        const double q = (5.0 * ir2) * (z[c] * z[c]);
+        const double fxy = fma(q, f, -f), fz = fma(q, f, -3.0 * f);
+        const double kxy = gk + fxy;
+        ax[c] = kxy * x[c]; ay[c] = kxy * y[c]; az[c] = (gk + fz) * z[c];
+        altitude[c] = fma(r2[c], ir[c], -KC(earth_r));
+    }
+    // geodetic pair iteration (geodetic_pair), merged over the two trajectories
+    double ip[2], A[2], B[2], zp[2], ke[2];
+    bool done[2];
+    RB_PAIR {
+        ip[c] = rb_rsqrt(p2[c]);
+        const double p = p2[c] * ip[c];
+        const double ta = z[c] * KC(earth_r), tb = p * KC(one_m_e2r);
+        const double th = rb_rsqrt(fma(ta, ta, tb * tb));
+        const double st = ta * th, ct = tb * th;
+        A[c] = fma(KC(e2r), st * (st * st), z[c]);
+        B[c] = fma(-KC(e2r), ct * (ct * ct), p);
+        zp[c] = z[c] * ip[c];
+        ke[c] = KC(e2r) * ip[c];
+    }
+    RB_PAIR {
+        const double q = rb_rsqrt(fma(B[c], B[c], KC(one_m_e2) * (A[c] * A[c])));
+        const double Bn = fma(-ke[c] * B[c], q, 1.0);
+        done[c] = fabs(fma(A[c], Bn, -(zp[c] * B[c]))) < KC(tan_tol) * fma(B[c], Bn, A[c] * zp[c]);
+        if (!done[c]) { A[c] = zp[c]; B[c] = Bn; }
+    }
+    if (!(done[0] && done[1])) {
+        double zp2[2], g[2], azp[2];
+        RB_PAIR { zp2[c] = zp[c] * zp[c]; g[c] = KC(one_m_e2) * zp2[c]; azp[c] = fabs(zp[c]); }
+        for (int it = 1; it < RB_GEODETIC_MAX_ITER; ++it) {
+            RB_PAIR {
+                const double q2 = rb_rsqrt(fma(B[c], B[c], g[c]));
+                const double Bn2 = fma(-ke[c] * B[c], q2, 1.0);
+                const bool conv = azp[c] * fabs(Bn2 - B[c]) < KC(tan_tol) * fma(B[c], Bn2, zp2[c]);
+                if (!done[c]) {          // a finished member keeps its (stale) iterate, as the scalar break does
+                    if (conv) done[c] = true;
+                    else B[c] = Bn2;
+                }
+            }
+            if (done[0] && done[1]) break;
+        }
+    }
+    // third bodies (fill the latency of the serial latitude -> density -> drag tail)
+    RB_PAIR {
+        {
+            const double dx = e[E_MOON + 0] - x[c], dy = e[E_MOON + 1] - y[c], dz = e[E_MOON + 2] - z[c];
+            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+            const double k3 = KC(moon_k) * (id * id * id);
+            const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
+            ax[c] += mx; ay[c] += my; az[c] += mz;
+        }
+        {
+            const double dx = e[E_SUN + 0] - x[c], dy = e[E_SUN + 1] - y[c], dz = e[E_SUN + 2] - z[c];
+            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+            const double k3 = KC(sun_k) * (id * id * id);
+            const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
+            ax[c] += sx; ay[c] += sy; az[c] += sz;
+        }
+    }
+    double lat_deg[2], rho[2];
+    RB_PAIR lat_deg[c] = pair_abs_latitude_deg(A[c], B[c]);
+    if (altitude[0] >= KC(blend_alt) && altitude[1] >= KC(blend_alt)) {
+        // both in the top layer above the solar-factor blend: the common branch of density(), pairwise
+        RB_PAIR {
+            const double latitude_factor = fma(KC(latc), lat_deg[c], 1.0);
+            rho[c] = (KC(top_rho0) * rb_exp((altitude[c] - KC(top_h)) * KC(top_k))) * (latitude_factor * e[E_SOLAR]);
+        }
+    } else {
+        double T;
+        RB_PAIR rho[c] = density(altitude[c], lat_deg[c], e[E_SOLAR], T);
+    }
+    RB_PAIR {
+        const double w2 = fma(wz[c], wz[c], fma(wx[c], wx[c], wy[c] * wy[c]));
+        const double vn = w2 * rb_rsqrt(w2);
+        const double kd = -(rho[c] * b[c].bc) * vn;
+        a[c][0] = fma(kd, wx[c], ax[c]); a[c][1] = fma(kd, wy[c], ay[c]); a[c][2] = fma(kd, wz[c], az[c]);
+    }
+}
+
 // event function of run_simulation.altitude_event (spacecraft_model.py:496-501)
 RB_HD double event_g(const double r[3], double event_altitude) {
     const double r2 = fma(r[2], r[2], fma(r[0], r[0], r[1] * r[1]));
