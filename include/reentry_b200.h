@@ -53,7 +53,8 @@ typedef enum rb_error {
 typedef enum rb_traj_status {
     RB_TRAJ_ALIVE = 0,     /* reached n_steps without an event */
     RB_TRAJ_IMPACTED = 1,  /* terminal altitude event fired (spacecraft_model.py:496-504) */
-    RB_TRAJ_NONFINITE = 2  /* state became NaN/Inf; lane retired */
+    RB_TRAJ_NONFINITE = 2, /* state became NaN/Inf; lane retired */
+    RB_TRAJ_STEP_FAILED = 3 /* adaptive mode only: step size below 10 ulp of t, or max_steps reached */
 } rb_traj_status;
 
 /* run flags */
@@ -210,6 +211,36 @@ int32_t rb_ground_track(rb_ctx *ctx, int64_t n, int64_t n_out, const double *sam
  * this is the rotated -- correct -- form, equal to the app's geodetic_coords[-1] convention.) */
 int32_t rb_impact_points(rb_ctx *ctx, int64_t n, const double *final_state, const double *impact_time,
                          const uint8_t *status, double t_end, double gmst0, double *out, void *stream);
+
+/* ---- adaptive mode: the reference's integrator AS SHIPPED ----------------
+ * run_simulation calls scipy.integrate.solve_ivp(method='RK45', rtol=1e-8, atol=1e-10, t_eval,
+ * events=[altitude_event]) (spacecraft_model.py:516).  One thread per trajectory, each on its own time
+ * axis: scipy's initial-step heuristic, error-controlled Dormand-Prince steps, terminal altitude event
+ * (Brent on the dense output) and samples at t_eval_k = t_eval0 + k*t_eval_dt (k < n_eval, <= the event
+ * time) interpolated on each step's quartic dense output.  Parity with the reference is at the level of
+ * the solver tolerance, not of rounding: the error norm is a cancellation of O(1e8), so accept/reject
+ * decisions and step sizes depend on summation order (the reference's own run depends on the host BLAS). */
+typedef struct rb_adaptive_run {
+    double t0, t_bound;          /* t_span */
+    double rtol, atol;           /* 1e-8, 1e-10 in the reference */
+    double t_eval0, t_eval_dt;   /* np.arange(ts, tf, dt), app.py:171 */
+    int64_t n_eval;
+    int64_t max_steps;           /* accepted + rejected attempts per trajectory */
+    double event_altitude;       /* 1000.0 */
+    double epoch_jd, gmst0;
+} rb_adaptive_run;
+
+typedef struct rb_adaptive_out {
+    double *samples;             /* [n_eval][8][n] via sample_stride / field_stride, or NULL */
+    int64_t sample_stride, field_stride;
+    double *final_state;         /* SoA [6][n] REQUIRED: dense-output state at the event, else state at t_bound */
+    double *impact_time;         /* [n] NaN = none, or NULL */
+    uint8_t *status;             /* [n] REQUIRED */
+    int32_t *n_samples, *n_accepted, *n_rejected; /* [n] or NULL */
+} rb_adaptive_out;
+
+int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_run *run, const rb_adaptive_out *out,
+                              void *stream);
 
 /* ---- host-buffer convenience (the end-to-end call of a ctypes / cgo style binding) ----
  * Everything is HOST memory (pinned memory from rb_host_alloc makes the copies asynchronous):

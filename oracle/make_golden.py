@@ -19,6 +19,7 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
                        100 km crossings of four O3 trajectories, from the reference's own functions
   thermal.npz          N1: thermal entries of the unmodified equations_of_motion dict + direct
                        spacecraft_temperature calls
+  adaptive.npz         N4: run_simulation as shipped (scipy adaptive RK45) on four launch geometries
   recorded_trajectory.json   first samples of the trajectory embedded in temperature_model.py:104-105
 
     python oracle/make_golden.py        # ~2-3 min (numba JIT of the reference leaves dominates)
@@ -312,6 +313,43 @@ def thermal(sm, const):
     return out
 
 
+def adaptive(sm, const):
+    """N4: SpacecraftModel.run_simulation AS SHIPPED (scipy adaptive RK45, rtol 1e-8, atol 1e-10, spacecraft_model.py:516)
+    on four launch geometries; plus the accepted-step times of the same solve_ivp call without t_eval."""
+    from scipy.integrate import solve_ivp
+
+    cases = [  # (Cd, A, m, gmst0, (v, lat, lon, alt, az, gamma), tf, dt_out)
+        (1.3, 14.0, 5000.0, 0.0, (7800, 0, 0, 120e3, 90, -1), 800, 1.0),            # C1
+        (2.2, 20.0, 500.0, 1.7, (7540, 45, -75, 500e3, 90, -2), 3700, 10.0),         # the app's defaults (app.py:37-54)
+        (2.2, 4.0, 800.0, 0.3, (7670, 51.6, 10, 400e3, 45, 0), 7200, 30.0),          # no event within the horizon
+        (1.3, 14.0, 5000.0, 2.9, (7000, -30, 40, 100e3, 120, -30), 200, 0.5),        # steep entry
+    ]
+    out = {"n_cases": len(cases)}
+    for k, (Cd, A, m, gmst0, geo, tf, dt) in enumerate(cases):
+        mdl = sm.SpacecraftModel(Cd=Cd, A=A, m=m, epoch=R.Epoch(EPOCH_JD), gmst0=gmst0, dt=10, iter_fact=2)
+        y0 = mdl.get_initial_state(*geo, gmst=gmst0)
+        t_eval = np.arange(0, tf, dt)
+        sol = mdl.run_simulation((0, tf), y0, t_eval)
+
+        def rhs(t, y):
+            dy = mdl.equations_of_motion(t, y)
+            return np.concatenate((dy["velocity"], dy["acceleration"]))
+
+        def ev(t, y):
+            return sm.euclidean_norm(y[0:3]) - const.EARTH_R - 1000.0
+        ev.terminal = True
+        ev.direction = -1
+        s2 = solve_ivp(rhs, (0, tf), y0, method="RK45", rtol=1e-8, atol=1e-10, events=[ev])
+        te = sol.t_events[0]
+        out.update({f"cfg_{k}": np.array([Cd, A, m, gmst0, tf, dt]), f"y0_{k}": y0, f"t_{k}": sol.t, f"y_{k}": sol.y,
+                    f"t_event_{k}": (te[0] if len(te) else np.nan),
+                    f"y_event_{k}": (sol.y_events[0][0] if len(te) else np.full(6, np.nan)),
+                    f"nfev_{k}": sol.nfev, f"status_{k}": sol.status, f"steps_t_{k}": s2.t,
+                    f"altitude_{k}": sol.additional_data["altitude"]})
+    out["epoch_jd"] = EPOCH_JD
+    return out
+
+
 def recorded_trajectory():
     """First samples of the trajectory recorded inside temperature_model.py:104-105 (10 s spacing;
     app defaults v=7540, 45N, 75W, 500 km, az 90, gamma -2).  Sample 0 pins get_initial_state
@@ -329,6 +367,9 @@ def recorded_trajectory():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     sm, cc, const = R.load()
+    if "--only-adaptive" in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "adaptive.npz"), **adaptive(sm, const))
+        return
     if "--only-thermal" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
         return
@@ -353,6 +394,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "edge.npz"), **edge_cases(const))
     np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
     np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
+    np.savez_compressed(os.path.join(GOLD, "adaptive.npz"), **adaptive(sm, const))
     with open(os.path.join(GOLD, "recorded_trajectory.json"), "w") as f:
         json.dump(recorded_trajectory(), f)
     print("wrote", sorted(os.listdir(GOLD)))

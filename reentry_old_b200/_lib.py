@@ -23,7 +23,7 @@ RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
 RB_DIAG_FIELDS = 23
 RB_THERMAL_FIELDS = 6
-TRAJ_ALIVE, TRAJ_IMPACTED, TRAJ_NONFINITE = 0, 1, 2
+TRAJ_ALIVE, TRAJ_IMPACTED, TRAJ_NONFINITE, TRAJ_STEP_FAILED = 0, 1, 2, 3
 
 vp = C.c_void_p
 i64 = C.c_int64
@@ -52,6 +52,16 @@ class RbThermal(C.Structure):
                 ("specific_heat_capacity", f64), ("emissivity", f64), ("ablation_efficiency", f64)]
 
 
+class RbAdaptiveRun(C.Structure):
+    _fields_ = [("t0", f64), ("t_bound", f64), ("rtol", f64), ("atol", f64), ("t_eval0", f64), ("t_eval_dt", f64),
+                ("n_eval", i64), ("max_steps", i64), ("event_altitude", f64), ("epoch_jd", f64), ("gmst0", f64)]
+
+
+class RbAdaptiveOut(C.Structure):
+    _fields_ = [("samples", vp), ("sample_stride", i64), ("field_stride", i64), ("final_state", vp), ("impact_time", vp),
+                ("status", vp), ("n_samples", vp), ("n_accepted", vp), ("n_rejected", vp)]
+
+
 class RbStats(C.Structure):
     _fields_ = [("kernel_launches", i64), ("propagate_launches", i64), ("steps_enqueued", i64),
                 ("last_polled_live", i64), ("propagate_ms", f64)]
@@ -76,6 +86,7 @@ SIGNATURES = {
                                 vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]),
     "rb_host_alloc": (vp, [i64]),
     "rb_host_free": (None, [vp]),
+    "rb_propagate_adaptive": (i32, [vp, C.POINTER(RbIn), C.POINTER(RbAdaptiveRun), C.POINTER(RbAdaptiveOut), vp]),
     "rb_ground_track": (i32, [vp, i64, i64, vp, i64, i64, vp, f64, f64, f64, f64, vp, vp, vp, vp, vp, vp]),
     "rb_impact_points": (i32, [vp, i64, vp, vp, vp, f64, f64, vp, vp]),
     "rb_math_probe": (i32, [vp, i32, i64, vp, vp, vp, vp]),

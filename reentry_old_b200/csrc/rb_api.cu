@@ -647,6 +647,31 @@ void rb_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+// ------------------------------------------------------------------ N4: adaptive mode
+int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_run *run, const rb_adaptive_out *out,
+                              void *stream) {
+    if (!ctx || !in || !run || !out) return RB_ERR_INVALID_ARG;
+    if (in->n < 0 || !in->y0 || !out->final_state || !out->status) return RB_ERR_INVALID_ARG;
+    if (!(run->rtol > 0) || !(run->atol >= 0) || !(run->t_bound >= run->t0) || run->n_eval < 0 || run->max_steps < 1)
+        return RB_ERR_INVALID_ARG;
+    if (in->n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    AdaptiveParams p{};
+    p.n = in->n; p.y0 = in->y0; p.y0_traj_stride = in->y0_traj_stride; p.y0_comp_stride = in->y0_comp_stride;
+    p.cd = in->cd; p.area = in->area; p.mass = in->mass;
+    p.cd_s = in->cd_scalar; p.area_s = in->area_scalar; p.mass_s = in->mass_scalar;
+    p.epoch_jd = run->epoch_jd; p.gmst0 = run->gmst0; p.t0 = run->t0; p.t_bound = run->t_bound;
+    p.rtol = std::max(run->rtol, 100 * 2.220446049250313e-16);   // validate_tol, common.py:44-51
+    p.atol = run->atol; p.t_eval0 = run->t_eval0; p.t_eval_dt = run->t_eval_dt; p.event_altitude = run->event_altitude;
+    p.n_eval = run->n_eval; p.max_steps = run->max_steps;
+    p.samples = out->samples; p.sample_stride = out->sample_stride; p.field_stride = out->field_stride;
+    p.final_state = out->final_state; p.impact_time = out->impact_time; p.status = out->status;
+    p.n_samples = out->n_samples; p.n_accepted = out->n_accepted; p.n_rejected = out->n_rejected;
+    k_adaptive<<<(unsigned)((in->n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return RB_OK;
+}
+
 // ------------------------------------------------------------------ N2: ground track
 int32_t rb_ground_track(rb_ctx *ctx, int64_t n, int64_t n_out, const double *samples, int64_t sample_stride,
                         int64_t field_stride, const int32_t *n_samples, double t0, double sample_dt, double gmst0,

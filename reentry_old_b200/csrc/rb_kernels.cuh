@@ -1001,6 +1001,174 @@ __global__ void k_impact_points(int64_t n, const double *final_state, const doub
     out[i] = lat; out[n + i] = lon; out[2 * n + i] = h;
 }
 
+// ---------------------------------------------------------------- N4: the reference's integrator as shipped
+// scipy.integrate.solve_ivp(method='RK45', rtol, atol, t_eval, events=[altitude_event]) as called by
+// run_simulation (spacecraft_model.py:516), one thread per trajectory, every trajectory on its own time
+// axis: select_initial_step (scipy _ivp/common.py:68-134), RungeKutta._step_impl (rk.py:111-176: RMS error
+// norm, SAFETY 0.9, factor clamp 0.2..10, no growth after a rejection, min step 10 ulp), events and t_eval
+// sampling on the quartic dense output (ivp.py:659-733).  Time-dependent inputs (Sun/Moon ephemeris, solar
+// factor) are evaluated at every stage time on the device (time_entry), since no two lanes share a time grid.
+struct AdaptiveParams {
+    int64_t n;
+    const double *y0;
+    int64_t y0_traj_stride, y0_comp_stride;
+    const double *cd, *area, *mass;
+    double cd_s, area_s, mass_s;
+    double epoch_jd, gmst0, t0, t_bound, rtol, atol, t_eval0, t_eval_dt, event_altitude;
+    int64_t n_eval, max_steps;
+    double *samples;
+    int64_t sample_stride, field_stride;
+    double *final_state;   // SoA [6][n]: state at the event time / at t_bound
+    double *impact_time;   // [n] NaN = none
+    uint8_t *status;       // [n] rb_traj_status
+    int32_t *n_samples, *n_accepted, *n_rejected;
+};
+
+__device__ __forceinline__ double rms6(const double x[6]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s = fma(x[i], x[i], s);
+    return sqrt(s) * 0.408248290463863 /* 1/sqrt(6) */;
+}
+
+__global__ void __launch_bounds__(64) k_adaptive(const AdaptiveParams p) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= p.n) return;
+    const double E[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+    const Body body = make_body(p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s);
+    double y[6], f[6], K[7][6], ynew[6], fnew[6], ent[ENTRY_DOUBLES];
+    auto rhs = [&](double t, const double *yy, double *dy) {
+        time_entry(t, p.epoch_jd, p.gmst0, ent);
+        double a[3];
+        acceleration<false>(ent, yy, yy + 3, body, a, nullptr);
+        dy[0] = yy[3]; dy[1] = yy[4]; dy[2] = yy[5]; dy[3] = a[0]; dy[4] = a[1]; dy[5] = a[2];
+    };
+#pragma unroll
+    for (int c = 0; c < 6; ++c) y[c] = p.y0[tid * p.y0_traj_stride + c * p.y0_comp_stride];
+    double t = p.t0;
+    rhs(t, y, f);
+    double h_abs;
+    {   // select_initial_step, order 4, direction +1, max_step inf
+        const double interval = fabs(p.t_bound - p.t0);
+        if (interval == 0.0) h_abs = 0.0;
+        else {
+            double scale[6], a[6], b[6], y1[6], f1[6];
+            for (int i = 0; i < 6; ++i) { scale[i] = p.atol + fabs(y[i]) * p.rtol; a[i] = y[i] / scale[i]; b[i] = f[i] / scale[i]; }
+            const double d0 = rms6(a), d1 = rms6(b);
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = fmin(h0, interval);
+            for (int i = 0; i < 6; ++i) y1[i] = fma(h0, f[i], y[i]);
+            rhs(t + h0, y1, f1);
+            for (int i = 0; i < 6; ++i) a[i] = (f1[i] - f[i]) / scale[i];
+            const double d2 = rms6(a) / h0;
+            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+            h_abs = fmin(fmin(100 * h0, h1), interval);
+        }
+    }
+    double g_old = event_g(y, p.event_altitude);
+    int64_t ei = 0;
+    int32_t acc = 0, rej = 0;
+    uint8_t status = RB_TRAJ_ALIVE;
+    double t_event = nan("");
+    while (true) {
+        if (t == p.t_bound) break;
+        if ((int64_t)acc + rej >= p.max_steps) { status = RB_TRAJ_STEP_FAILED; break; }
+        const double min_step = 10 * fabs(nextafter(t, (double)INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false, failed = false;
+        double h = 0, t_new = t;
+        for (;;) {
+            if (h_abs < min_step) { failed = true; break; }
+            t_new = t + h_abs;
+            if (t_new - p.t_bound > 0) t_new = p.t_bound;
+            h = t_new - t;
+            h_abs = fabs(h);
+            for (int i = 0; i < 6; ++i) K[0][i] = f[i];
+#pragma unroll 1
+            for (int s = 1; s < 6; ++s) {
+                double ys[6];
+                for (int i = 0; i < 6; ++i) {
+                    double dy = c_T.a[s][0] * K[0][i];
+                    for (int j = 1; j < s; ++j) dy = fma(c_T.a[s][j], K[j][i], dy);
+                    ys[i] = fma(dy, h, y[i]);
+                }
+                rhs(t + c_T.c[s] * h, ys, K[s]);
+            }
+            for (int i = 0; i < 6; ++i) {
+                double sacc = c_T.a[6][0] * K[0][i];
+                for (int j = 1; j < 6; ++j) sacc = fma(c_T.a[6][j], K[j][i], sacc);
+                ynew[i] = fma(h, sacc, y[i]);
+            }
+            rhs(t + h, ynew, fnew);
+            for (int i = 0; i < 6; ++i) K[6][i] = fnew[i];
+            double en[6];
+            for (int i = 0; i < 6; ++i) {
+                double e = K[0][i] * E[0];
+                for (int j = 1; j < 7; ++j) e = fma(K[j][i], E[j], e);
+                const double scale = p.atol + fmax(fabs(y[i]), fabs(ynew[i])) * p.rtol;
+                en[i] = e * h / scale;
+            }
+            const double error_norm = rms6(en);
+            if (error_norm < 1) {
+                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                break;
+            }
+            if (!(error_norm >= 1)) { failed = true; status = RB_TRAJ_NONFINITE; break; }   // NaN error norm
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, -0.2));
+            rejected = true;
+            ++rej;
+        }
+        if (failed) { if (status == RB_TRAJ_ALIVE) status = RB_TRAJ_STEP_FAILED; break; }
+        ++acc;
+        Dense d;
+        for (int c = 0; c < 6; ++c) {
+            for (int k = 0; k < 4; ++k) {
+                double q = 0.0;
+                for (int j = 0; j < 7; ++j) q += K[j][c] * c_P[j][k];
+                d.Q[c][k] = q;
+            }
+            d.y_old[c] = y[c];
+        }
+        d.t_old = t; d.h = h; d.event_altitude = p.event_altitude;
+        const double g_new = event_g(ynew, p.event_altitude);
+        double t_lim = t_new;
+        bool terminate = false;
+        if (g_old >= 0.0 && g_new <= 0.0) {
+            t_event = brent_event(d, t, t_new);
+            terminate = true;
+            t_lim = t_event;
+        }
+        while (ei < p.n_eval) {
+            const double te = p.t_eval0 + p.t_eval_dt * (double)ei;
+            if (te > t_lim) break;
+            if (p.samples) {
+                double ye[6];
+                d.eval(te, ye);
+                double *sp = p.samples + ei * p.sample_stride + tid;
+                for (int c = 0; c < 6; ++c) sp[c * p.field_stride] = ye[c];
+                sp[6 * p.field_stride] = sqrt(ye[0] * ye[0] + ye[1] * ye[1] + ye[2] * ye[2]) - RB_EARTH_R;
+                sp[7 * p.field_stride] = sqrt(ye[3] * ye[3] + ye[4] * ye[4] + ye[5] * ye[5]);
+            }
+            ++ei;
+        }
+        if (terminate) {
+            d.eval(t_event, y);
+            status = RB_TRAJ_IMPACTED;
+            break;
+        }
+        for (int c = 0; c < 6; ++c) { y[c] = ynew[c]; f[c] = fnew[c]; }
+        t = t_new; g_old = g_new;
+    }
+    for (int c = 0; c < 6; ++c) p.final_state[c * p.n + tid] = y[c];
+    if (p.impact_time) p.impact_time[tid] = t_event;
+    p.status[tid] = status;
+    if (p.n_samples) p.n_samples[tid] = (int32_t)ei;
+    if (p.n_accepted) p.n_accepted[tid] = acc;
+    if (p.n_rejected) p.n_rejected[tid] = rej;
+}
+
 // ---------------------------------------------------------------- self-test of rb_math.cuh
 __global__ void k_math_probe(int op, int64_t n, const double *x, const double *y, double *out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -145,7 +145,7 @@ class OdeResultLike(dict):
 
 class SpacecraftModel:
     def __init__(self, Cd=2.2, A=20.0, m=500.0, epoch=None, gmst0=0.0, sim_type="RK45",
-                 material=(233, 1, 1, 0.1), dt=10, iter_fact=2, device=None):
+                 material=(233, 1, 1, 0.1), dt=10, iter_fact=2, device=None, integrator="fixed"):
         # same attributes as spacecraft_model.py:394-410
         self.Cd = Cd
         self.A = A
@@ -164,6 +164,10 @@ class SpacecraftModel:
         self.dt = dt
         self.iter_fact = iter_fact
         self.device = device
+        if integrator not in ("fixed", "adaptive"):
+            raise ValueError("integrator must be 'fixed' (fixed-step Dormand-Prince, the ensemble hot path) or "
+                             "'adaptive' (scipy's error-controlled RK45 exactly as the reference calls it)")
+        self.integrator = integrator
 
     # ------------------------------------------------------------------------- plumbing
     def _ctx(self) -> DeviceContext:
@@ -356,8 +360,60 @@ class SpacecraftModel:
                                            out.data_ptr(), stream), "rb_impact_points")
         return out
 
+    # ------------------------------------------------------------ adaptive mode (N4)
+    def run_ensemble_adaptive(self, y0, t_span, t_eval_dt, n_eval=None, rtol=1e-8, atol=1e-10, Cd=None, A=None, m=None,
+                              store_samples=True, max_steps=1_000_000, event_altitude=1000.0) -> EnsembleResult:
+        """The reference's integrator as shipped (solve_ivp RK45, rtol 1e-8, atol 1e-10, spacecraft_model.py:516)
+        for N independent initial states, each on its own adaptive time axis.  Samples are the dense-output
+        values at t_span[0] + k * t_eval_dt (k < n_eval; default: np.arange(t0, tf, dt), app.py:171) that
+        are not after the terminal altitude event."""
+        torch = _torch()
+        ctx = self._ctx()
+        if self.sim_type != "RK45":
+            raise NotImplementedError("only RK45 is implemented on this path")
+        t0, tf = float(t_span[0]), float(t_span[1])
+        if n_eval is None:
+            n_eval = len(np.arange(t0, tf, t_eval_dt))
+        if not (isinstance(y0, torch.Tensor) and y0.is_cuda and y0.dtype == torch.float64 and y0.ndim == 2):
+            y0 = self._dev(y0)
+        if y0.ndim == 1:
+            y0 = y0.reshape(1, 6)
+        n = y0.shape[0]
+        dev = y0.device
+        samples = torch.full((n_eval, L.RB_SAMPLE_FIELDS, n), float("nan"), dtype=torch.float64, device=dev) \
+            if store_samples else None
+        final_state = torch.empty((6, n), dtype=torch.float64, device=dev)
+        impact_time = torch.empty(n, dtype=torch.float64, device=dev)
+        status = torch.empty(n, dtype=torch.uint8, device=dev)
+        n_samples = torch.empty(n, dtype=torch.int32, device=dev)
+        n_acc = torch.empty(n, dtype=torch.int32, device=dev)
+        n_rej = torch.empty(n, dtype=torch.int32, device=dev)
+        arr = [None if a is None else self._dev(a, n) for a in (Cd, A, m)]
+        rin = L.RbIn(n=n, y0=y0.data_ptr(), y0_traj_stride=y0.stride(0), y0_comp_stride=y0.stride(1),
+                     cd=None if arr[0] is None else arr[0].data_ptr(), area=None if arr[1] is None else arr[1].data_ptr(),
+                     mass=None if arr[2] is None else arr[2].data_ptr(),
+                     cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
+        run = L.RbAdaptiveRun(t0=t0, t_bound=tf, rtol=float(rtol), atol=float(atol), t_eval0=t0, t_eval_dt=float(t_eval_dt),
+                              n_eval=int(n_eval), max_steps=int(max_steps), event_altitude=float(event_altitude),
+                              epoch_jd=self.epoch, gmst0=self.gmst0)
+        out = L.RbAdaptiveOut(samples=None if samples is None else samples.data_ptr(), sample_stride=L.RB_SAMPLE_FIELDS * n,
+                              field_stride=n, final_state=final_state.data_ptr(), impact_time=impact_time.data_ptr(),
+                              status=status.data_ptr(), n_samples=n_samples.data_ptr(), n_accepted=n_acc.data_ptr(),
+                              n_rejected=n_rej.data_ptr())
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        if n > 0:
+            ctx.check(ctx.lib.rb_propagate_adaptive(ctx.handle, C.byref(rin), C.byref(run), C.byref(out), stream),
+                      "rb_propagate_adaptive")
+        res = EnsembleResult(t=t0 + float(t_eval_dt) * np.arange(n_eval), samples=samples, final_state=final_state,
+                             impact_step=n_acc, impact_time=impact_time, status=status, n_samples=n_samples,
+                             dt=float(t_eval_dt), out_stride=1, n_steps=int(n_eval) - 1,
+                             stats=dict(kernel_launches=1, propagate_launches=1, steps_enqueued=0, last_polled_live=-1,
+                                        propagate_ms=0.0))
+        res.n_accepted, res.n_rejected = n_acc, n_rej
+        return res
+
     # ------------------------------------------------------------------ run_simulation
-    def run_simulation(self, t_span, y0, t_eval, progress_callback=None, max_step=None):
+    def run_simulation(self, t_span, y0, t_eval, progress_callback=None, max_step=None, integrator=None):
         """spacecraft_model.py:490-519 for ONE trajectory, fixed-step contract.
 
         `t_eval` must be a uniform grid starting at t_span[0] (the app builds
@@ -371,6 +427,8 @@ class SpacecraftModel:
         t0, tf = float(t_span[0]), float(t_span[1])
         if t_eval.ndim != 1 or t_eval.size < 1:
             raise ValueError("t_eval must be a non-empty 1-D grid")
+        if (integrator or self.integrator) == "adaptive":
+            return self._run_simulation_adaptive(t0, tf, y0, t_eval, progress_callback)
         if t_eval.size > 1:
             spacing = float(t_eval[1] - t_eval[0])
             if not np.allclose(np.diff(t_eval), spacing, rtol=1e-9, atol=1e-12) or spacing <= 0:
@@ -407,6 +465,41 @@ class SpacecraftModel:
         sol.nlu = 0
         sol.sol = None
         # additional_data: re-evaluate the RHS at every output sample, as the reference does (:517-518)
+        d = self.equations_of_motion_batch(sol.t, samples[:, :6]) if n_valid else {}
+        sol.additional_data = {k: v_.cpu().numpy().copy() for k, v_ in d.items()}
+        if progress_callback is not None:
+            progress_callback(1.0, time.time() - self.start_time)
+        return sol
+
+    def _run_simulation_adaptive(self, t0, tf, y0, t_eval, progress_callback):
+        """run_simulation with the reference's own integrator (adaptive RK45, rtol 1e-8, atol 1e-10)."""
+        if t_eval.size > 1:
+            spacing = float(t_eval[1] - t_eval[0])
+            if not np.allclose(np.diff(t_eval), spacing, rtol=1e-9, atol=1e-12) or spacing <= 0:
+                raise ValueError("t_eval must be uniformly spaced (np.arange(ts, tf, dt), app.py:171)")
+        else:
+            spacing = max(tf - t0, 1.0)
+        if abs(t_eval[0] - t0) > 1e-9 * max(1.0, abs(t0)):
+            raise ValueError("t_eval must start at t_span[0]")
+        res = self.run_ensemble_adaptive(np.asarray(y0, dtype=np.float64).reshape(1, 6), (t0, tf), spacing, n_eval=t_eval.size)
+        n_valid = int(res.n_samples[0].item())
+        samples = res.samples[:n_valid, :, 0].cpu().numpy()
+        status = int(res.status[0].item())
+        hit = status == L.TRAJ_IMPACTED
+        sol = OdeResultLike()
+        sol.t = t_eval[:n_valid].copy()
+        sol.y = np.ascontiguousarray(samples[:, :6].T)
+        sol.t_events = [np.array([float(res.impact_time[0].item())]) if hit else np.array([]), np.array([])]
+        sol.y_events = [res.final_state[:, 0].cpu().numpy()[None, :] if hit else np.empty((0, 6)), np.empty((0, 6))]
+        sol.status = 1 if hit else (0 if status == L.TRAJ_ALIVE else -1)
+        sol.success = status in (L.TRAJ_ALIVE, L.TRAJ_IMPACTED)
+        sol.message = ("A termination event occurred." if hit else
+                       "The solver successfully reached the end of the integration interval." if sol.success
+                       else "Required step size is less than spacing between numbers.")
+        sol.nfev = 2 + 6 * (int(res.n_accepted[0].item()) + int(res.n_rejected[0].item()))
+        sol.njev = 0
+        sol.nlu = 0
+        sol.sol = None
         d = self.equations_of_motion_batch(sol.t, samples[:, :6]) if n_valid else {}
         sol.additional_data = {k: v_.cpu().numpy().copy() for k, v_ in d.items()}
         if progress_callback is not None:
