@@ -180,7 +180,9 @@ int32_t rb_build_time_table(double epoch_jd, double gmst0, double t0, double dt,
     for (int64_t n = 0; n <= n_steps; ++n) { tn[(size_t)n] = t; t = t + dt; }
     const int64_t n_entries = rb_time_table_entries(n_steps);
 #ifdef _OPENMP
-    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    // torchrun exports OMP_NUM_THREADS=1 to every rank; the table build is a short burst, so size the team from
+    // the machine (capped) rather than from that variable
+    if (n_threads <= 0) n_threads = std::max(omp_get_max_threads(), std::min(omp_get_num_procs(), 16));
 #pragma omp parallel for schedule(static) num_threads(n_threads) if (n_entries > 512)
 #endif
     for (int64_t e = 0; e < n_entries; ++e) {
