@@ -56,14 +56,16 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(steps, op=dist.ReduceOp.SUM)
     if rank == 0:
-        lat, lon = allp[:, 0], allp[:, 1]
+        hit = ~torch.isnan(allp[:, 3])
+        lat, lon = allp[hit, 0], allp[hit, 1]
         print(json.dumps({"config": f"C5 reentry dispersion, {n_total} trajectories over {world} GPU(s)", "n_total": n_total,
                           "n_gpus": world, "seconds": ms.item() * 1e-3, "traj_steps": steps.item(),
                           "traj_steps_per_s": steps.item() / (ms.item() * 1e-3), "gathered_rows": int(allp.shape[0]),
                           "gather_bytes": int(allp.numel() * 8),
                           "impact_lat_mean_std": [lat.mean().item(), lat.std().item()],
                           "impact_lon_mean_std": [lon.mean().item(), lon.std().item()],
-                          "checksum": float(allp[:, 3].sum().item())}))
+                          "not_impacted_within_cap": int(torch.isnan(allp[:, 3]).sum().item()),
+                          "checksum": float(torch.nansum(allp[:, 3]).item())}))
     if world > 1:
         dist.destroy_process_group()
 
