@@ -46,7 +46,8 @@ FLOP_PER_TRAJ_STEP, FLOP_SOURCE = _flop_per_traj_step()
 def _ncu_pipe_numbers():
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "flop_per_traj_step.json")))
-        return {k: d[k] for k in ("fp64_pipe_busy_pct_ncu", "fp64_share_of_issued_pct_ncu", "issue_active_pct_ncu") if k in d}
+        return {k: d[k] for k in ("fp64_pipe_busy_pct_ncu", "fp64_share_of_issued_pct_ncu", "issue_active_pct_ncu",
+                                  "dram_bytes_per_traj_step_ncu") if k in d}
     except Exception:
         return {}
 SAMPLE_BYTES = 64
@@ -267,10 +268,13 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ncu_nums = _ncu_pipe_numbers()
+    traffic = (ncu_nums["dram_bytes_per_traj_step_ncu"] * steps_per_pass / max(1, n_prop)
+               if "dram_bytes_per_traj_step_ncu" in ncu_nums else None)   # DRAM bytes per k_propagate launch (state only)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_propagate", "kernel_ms_per_pass": kern_ms, "kernel_launches_per_pass": n_prop,
+                "traffic": traffic, "kernel": "k_propagate", "kernel_ms_per_pass": kern_ms, "kernel_launches_per_pass": n_prop,
                 "kernel_share_of_step": kern_ms / (ms / K), "flop_per_traj_step": FLOP_PER_TRAJ_STEP, "flop_source": FLOP_SOURCE,
-                "ncu": _ncu_pipe_numbers(),
+                "ncu": ncu_nums,
                 "peak_source": "DFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 figure); "
                                "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
                 "output_write": {"bytes_per_pass": sample_bytes, "achieved_gbs": sample_bytes / (kern_ms * 1e-3) / 1e9,

@@ -1,7 +1,7 @@
-"""Run the BASELINE.json configurations C1..C4 on the GPU box: throughput + parity of a subsample
+"""TEST INFRASTRUCTURE (uses the CPU oracle as the checker; not collected by pytest).  Run the BASELINE.json configurations C1..C4 on the GPU box: throughput + parity of a subsample
 against the CPU oracle (compared horizon of SURVEY.md 7.2(5)) + full-horizon drift.
 
-    python tools/run_configs.py [c1 c2 c3 c4] [--scale 1.0]   -> one JSON line per config
+    python tests/run_configs.py [c1 c2 c3 c4] [--scale 1.0]   -> one JSON line per config
 """
 import json
 import os
