@@ -1,18 +1,25 @@
 // rb_kernels.cuh -- sm_100a kernels of the ensemble propagator.
 //
 //   k_init            copy y0 -> in-place state (SoA), identity live list, sample 0
-//   k_propagate       THE hot kernel: one FP64 thread per live trajectory, fixed-step
-//                     Dormand-Prince (scipy RK45 tableau, FSAL), time-table tiles staged into
-//                     shared memory with cp.async.bulk (TMA bulk copy) + mbarrier, double
-//                     buffered; stage derivatives K0..K6 parked in shared memory so that
-//                     the register budget buys occupancy; warp-vote retirement of impacted
-//                     lanes; SoA streaming stores of the decimated samples
+//   k_propagate       THE hot kernel: one FP64 thread per live trajectory, fixed-step Dormand-Prince
+//                     (scipy RK45 tableau, FSAL, Nystrom stage form), time-table tiles staged into shared
+//                     memory with cp.async.bulk (TMA bulk copy) + mbarrier, double buffered; the
+//                     acceleration rows Ka_0..Ka_6 of the stage derivatives parked in shared memory so
+//                     that 80 registers buy 24 resident warps; warp-vote retirement of impacted lanes;
+//                     SoA streaming stores of the decimated samples (to HBM or straight to pinned host
+//                     memory).  Template bool SKIP = RB_FLAG_SKIP_NEGLIGIBLE_DRAG instantiation.
+//   k_propagate2      the same arithmetic for two trajectories per thread (opt-in experiment)
 //   k_count_live / k_scan_blocks / k_scatter_live
 //                     order-preserving compaction of the live-trajectory index list
-//   k_refine          impact-time refinement on the step's quartic dense output (Brent)
-//   k_initial_states  batched get_initial_state
-//   k_eom             per-sample diagnostics (equations_of_motion dict)
-//   k_dfma_peak       FP64 FMA peak probe for the roofline denominator
+//   k_refine          impact-time refinement on the step's quartic dense output (Brent), n_samples
+//   k_adaptive        N4: scipy's error-controlled RK45 as run_simulation calls it, one thread per trajectory
+//   k_initial_states / k_dispersed_states
+//                     batched get_initial_state; N3 counter-based (Philox4x32-10) dispersion generator
+//   k_eom             N1 per-sample diagnostics (equations_of_motion dict incl. the thermal entries)
+//   k_ground_track / k_impact_points
+//                     N2 the app's post-pass (geodetic coordinates, haversine down-range, crossings)
+//   k_math_probe, k_dfma_peak
+//                     self-test of rb_math.cuh; FP64 FMA peak probe for the roofline denominator
 #pragma once
 
 #include <cuda_runtime.h>
