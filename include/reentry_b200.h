@@ -73,6 +73,10 @@ typedef enum rb_traj_status {
 #define RB_OVERLAP_MIN_TRAJECTORIES 600000
 #define RB_FLAG_PAIRWISE_KERNEL 128u /* use the two-trajectories-per-thread step kernel while a partition has >= 200k
                                    live trajectories (bit-identical results; off by default: not faster on B200) */
+#define RB_FLAG_RESUME 256u       /* checkpoint / resume: continue a run whose previous chunk ended at table step
+                                   `first_step` (a multiple of out_stride).  in->y0 is ignored; out->final_state,
+                                   status, impact_step, impact_time (and samples, indexed by the absolute step) are the
+                                   buffers the previous chunk wrote.  Chunked runs equal the one-shot run bit for bit */
 #define RB_FLAG_STAGED_SAMPLES 64u /* rb_propagate_host: never write samples directly into pinned host memory */
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */

@@ -19,6 +19,7 @@ RB_FLAG_SKIP_NEGLIGIBLE_DRAG = 16
 RB_FLAG_NO_OVERLAP = 32
 RB_FLAG_STAGED_SAMPLES = 64
 RB_FLAG_PAIRWISE_KERNEL = 128
+RB_FLAG_RESUME = 256
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
 RB_DIAG_FIELDS = 23

@@ -15,8 +15,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libreentry_b200.so")
 SOURCES = [os.path.join(CSRC, "rb_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "rb_kernels.cuh"), os.path.join(CSRC, "rb_physics.cuh"),
-                  os.path.join(ROOT, "include", "reentry_b200.h"), os.path.join(ROOT, "include", "reentry_constants.h")]
+DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + \
+    [os.path.join(ROOT, "include", "reentry_b200.h"), os.path.join(ROOT, "include", "reentry_constants.h")]
 
 
 def nvcc_path() -> str:

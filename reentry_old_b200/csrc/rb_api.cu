@@ -312,12 +312,16 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     if (!ctx || !in || !run || !out) return RB_ERR_INVALID_ARG;
     const int64_t n = in->n;
     if (n < 0 || n > 0x7fffffffLL) return RB_ERR_INVALID_ARG;
-    if (!in->y0 || !out->final_state || !out->status || !out->impact_step) return RB_ERR_INVALID_ARG;
+    const bool resume = (run->flags & RB_FLAG_RESUME) != 0;
+    if ((!in->y0 && !resume) || !out->final_state || !out->status || !out->impact_step) return RB_ERR_INVALID_ARG;
+    if (resume && (run->first_step % run->out_stride) != 0) return RB_ERR_INVALID_ARG;
     if (run->n_steps < 0 || run->first_step < 0 || run->out_stride < 1 || run->out_stride > 0x7fffffffLL)
         return RB_ERR_INVALID_ARG;
     if (ctx->table_steps < 0) return RB_ERR_NO_TIME_TABLE;
     if (run->first_step + run->n_steps > ctx->table_steps) return RB_ERR_TABLE_RANGE;
-    if (out->samples && out->n_out_capacity < run->n_steps / run->out_stride + 1) return RB_ERR_INVALID_ARG;
+    // sample frame: a resumed run indexes samples by the ABSOLUTE (table-frame) step, so that all chunks fill one buffer
+    const int64_t frame0 = (run->flags & RB_FLAG_RESUME) ? run->first_step : 0;
+    if (out->samples && out->n_out_capacity < (frame0 + run->n_steps) / run->out_stride + 1) return RB_ERR_INVALID_ARG;
     ctx->stats = rb_stats{0, 0, 0, -1, 0.0};
     if (steps_done_out) *steps_done_out = 0;
     if (n == 0) return RB_OK;
@@ -352,7 +356,8 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     ip.state = out->final_state; ip.n = n; ip.live = ctx->d_live[0];
     ip.impact_step = out->impact_step; ip.impact_time = out->impact_time; ip.status = out->status;
     ip.samples = out->samples; ip.sample_stride = out->sample_stride; ip.field_stride = out->field_stride;
-    k_init<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ip);
+    if (resume) k_init_resume<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ctx->d_live[0], n);
+    else k_init<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ip);
     k_set_counts<<<1, 1, 0, stream>>>(parts[0].n_live, (int32_t)parts[0].count, n_parts > 1 ? parts[1].n_live : nullptr,
                                      n_parts > 1 ? (int32_t)parts[1].count : 0);
     CK(cudaMemsetAsync(ctx->d_n_live + 8, 0, sizeof(int32_t), stream));  // edge-sample counter of k_refine
@@ -393,7 +398,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
         }
         const int64_t steps = std::min<int64_t>(spl, run->n_steps - done);
         sp.table_step0 = run->first_step + done;
-        sp.run_step0 = done;
+        sp.run_step0 = frame0 + done;
         sp.n_launch_steps = (int)steps;
         cudaStream_t active[2];
         int n_active = 0;
@@ -453,7 +458,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     rp.impact_step = out->impact_step; rp.impact_time = out->impact_time; rp.status = out->status;
     rp.n_samples = out->n_samples;
     rp.samples = out->samples; rp.sample_stride = out->sample_stride; rp.field_stride = out->field_stride;
-    rp.out_stride = run->out_stride; rp.run_first_step = run->first_step; rp.run_n_steps = run->n_steps;
+    rp.out_stride = run->out_stride; rp.run_first_step = run->first_step - frame0; rp.run_n_steps = frame0 + run->n_steps;
     rp.refine = (run->flags & RB_FLAG_NO_REFINE) ? 0 : 1;
     rp.edge_count = ctx->d_n_live + 8;
     k_refine<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(rp);

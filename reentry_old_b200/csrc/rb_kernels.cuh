@@ -158,6 +158,11 @@ struct InitParams {
     int64_t sample_stride, field_stride;
 };
 
+__global__ void k_init_resume(int32_t *live, int64_t n) {   // RB_FLAG_RESUME: the buffers ARE the checkpoint
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) live[i] = (int32_t)i;
+}
+
 __global__ void k_init(const InitParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
@@ -723,7 +728,8 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
         const int64_t local_prev = (int64_t)p.impact_step[tid] - 1 - p.run_first_step;  // last completed step
         ns = (int32_t)(local_prev / p.out_stride + 1);
     }
-    if (st == RB_TRAJ_IMPACTED && p.refine && p.impact_step && p.impact_time) {
+    // (an impact refined by an earlier chunk of a resumed run has a finite impact_time and is left alone)
+    if (st == RB_TRAJ_IMPACTED && p.refine && p.impact_step && p.impact_time && p.impact_time[tid] != p.impact_time[tid]) {
         const int64_t n_abs = (int64_t)p.impact_step[tid] - 1;
         const double *e0 = p.table + (RB_STAGES_PER_STEP * n_abs) * ENTRY_DOUBLES;
         const Body body = make_body(p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s);

@@ -360,6 +360,54 @@ class SpacecraftModel:
                                            out.data_ptr(), stream), "rb_impact_points")
         return out
 
+    # ------------------------------------------------------------ checkpoint / resume
+    def run_ensemble_chunked(self, y0, dt, n_steps, chunk_steps, t0=0.0, out_stride=1, Cd=None, A=None, m=None,
+                             store_samples=True, event_altitude=1000.0):
+        """Generator: propagate in chunks of `chunk_steps` (a multiple of out_stride) and yield the SAME
+        EnsembleResult after every chunk -- its tensors are the checkpoint (state, status, impact step / time,
+        samples filled so far), so a long run can be streamed, inspected or stopped and continued.  The
+        concatenation of the chunks equals run_ensemble(n_steps) bit for bit."""
+        torch = _torch()
+        ctx = self._ctx()
+        if chunk_steps < 1 or chunk_steps % out_stride:
+            raise ValueError("chunk_steps must be a positive multiple of out_stride")
+        y0 = self._dev(y0) if not (isinstance(y0, torch.Tensor) and y0.is_cuda and y0.dtype == torch.float64) else y0
+        y0 = y0.reshape(-1, 6)
+        n, dev = y0.shape[0], y0.device
+        stream = torch.cuda.current_stream(ctx.device).cuda_stream
+        ctx.stage_time_table(self.epoch, self.gmst0, float(t0), float(dt), int(n_steps), stream)
+        n_out = n_steps // out_stride + 1
+        samples = torch.full((n_out, L.RB_SAMPLE_FIELDS, n), float("nan"), dtype=torch.float64, device=dev) \
+            if store_samples else None
+        res = EnsembleResult(t=float(t0) + float(dt) * out_stride * np.arange(n_out), samples=samples,
+                             final_state=torch.empty((6, n), dtype=torch.float64, device=dev),
+                             impact_step=torch.empty(n, dtype=torch.int32, device=dev),
+                             impact_time=torch.empty(n, dtype=torch.float64, device=dev),
+                             status=torch.empty(n, dtype=torch.uint8, device=dev),
+                             n_samples=torch.empty(n, dtype=torch.int32, device=dev), dt=float(dt), out_stride=int(out_stride),
+                             n_steps=0)
+        arr = [None if a is None else self._dev(a, n) for a in (Cd, A, m)]
+        rin = L.RbIn(n=n, y0=y0.data_ptr(), y0_traj_stride=y0.stride(0), y0_comp_stride=y0.stride(1),
+                     cd=None if arr[0] is None else arr[0].data_ptr(), area=None if arr[1] is None else arr[1].data_ptr(),
+                     mass=None if arr[2] is None else arr[2].data_ptr(),
+                     cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
+        out = L.RbOut(samples=None if samples is None else samples.data_ptr(), sample_stride=L.RB_SAMPLE_FIELDS * n,
+                      field_stride=n, n_out_capacity=n_out, final_state=res.final_state.data_ptr(),
+                      impact_step=res.impact_step.data_ptr(), impact_time=res.impact_time.data_ptr(),
+                      status=res.status.data_ptr(), n_samples=res.n_samples.data_ptr())
+        done = 0
+        while done < n_steps:
+            steps = min(chunk_steps, n_steps - done)
+            flags = L.RB_FLAG_COMPACT | L.RB_FLAG_EARLY_EXIT | (L.RB_FLAG_RESUME if done else 0)
+            run = L.RbRun(first_step=done, n_steps=steps, out_stride=int(out_stride), steps_per_launch=0,
+                          event_altitude=float(event_altitude), flags=flags)
+            if n > 0:
+                ctx.check(ctx.lib.rb_propagate(ctx.handle, C.byref(rin), C.byref(run), C.byref(out), stream), "rb_propagate")
+            done += steps
+            res.n_steps = done
+            res.stats = ctx.stats()
+            yield res
+
     # ------------------------------------------------------------ adaptive mode (N4)
     def run_ensemble_adaptive(self, y0, t_span, t_eval_dt, n_eval=None, rtol=1e-8, atol=1e-10, Cd=None, A=None, m=None,
                               store_samples=True, max_steps=1_000_000, event_altitude=1000.0) -> EnsembleResult:

@@ -251,6 +251,28 @@ def test_pairwise_kernel_is_bit_identical(Model, torch, oracle):
     assert np.array_equal(a.impact_step[sub].cpu().numpy(), ref["impact_step"])
 
 
+def test_checkpoint_resume_equals_one_shot(Model, torch):
+    """RB_FLAG_RESUME: the output buffers are the checkpoint; chunked propagation == one call, bit for bit."""
+    from reentry_old_b200.configs import reentry_dispersion_params
+
+    n, n_steps, stride = 4000, 2048, 16
+    p = reentry_dispersion_params(n, seed=41)
+    p[::5, 5] -= 0.8                                   # impacts spread over several chunks
+    m = Model(Cd=1.3, A=14.0, m=5000.0)
+    y0 = m.get_initial_states(*p.T)
+    one = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=stride)
+    for chunk in (16, 336, 1024, 4096):
+        seen = []
+        for res in m.run_ensemble_chunked(y0, 0.5, n_steps, chunk, out_stride=stride):
+            seen.append(int((res.status == 1).sum()))
+        assert seen == sorted(seen) and seen[-1] == int((one.status == 1).sum())
+        assert res.n_steps == n_steps
+        assert torch.equal(torch.nan_to_num(res.samples, nan=-1.0), torch.nan_to_num(one.samples, nan=-1.0)), chunk
+        for k in ("final_state", "impact_step", "status", "n_samples"):
+            assert torch.equal(getattr(res, k), getattr(one, k)), (chunk, k)
+        assert torch.equal(torch.nan_to_num(res.impact_time), torch.nan_to_num(one.impact_time)), chunk
+
+
 def test_soa_input_and_per_trajectory_bodies(Model, torch, oracle):
     rng = np.random.default_rng(8)
     n = 300
