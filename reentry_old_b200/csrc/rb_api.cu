@@ -370,7 +370,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     }
 
     StepParams sp{};
-    sp.table = ctx->d_table; sp.out_stride = run->out_stride; sp.h = ctx->dt; sp.event_altitude = run->event_altitude;
+    sp.table = ctx->d_table; sp.out_stride = run->out_stride; sp.h = ctx->dt; sp.ht = make_htableau(ctx->dt); sp.event_altitude = run->event_altitude;
     sp.state = out->final_state; sp.n = n;
     sp.cd = in->cd; sp.area = in->area; sp.mass = in->mass;
     sp.cd_s = in->cd_scalar; sp.area_s = in->area_scalar; sp.mass_s = in->mass_scalar;
@@ -450,7 +450,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     if (profile) CK(cudaEventRecord(ctx->span_ev[1], stream));
 
     RefineParams rp{};
-    rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.event_altitude = run->event_altitude;
+    rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.ht = make_htableau(ctx->dt); rp.event_altitude = run->event_altitude;
     rp.skip_drag = skip_drag ? 1 : 0;
     rp.state = out->final_state; rp.n = n;
     rp.cd = in->cd; rp.area = in->area; rp.mass = in->mass;

@@ -46,42 +46,47 @@ constexpr int K_ROWS = 3;
 __constant__ Tableau c_T = make_tableau();  // run-time operands from the constant bank
 __constant__ double c_P[7][4] = {RB_DP_P_ROWS};
 
-// Stage state of stage S (1..6; 6 = the step's end point, row 6 of A = B):
-//   v_s = v_n + h sum_j a_sj Ka_j ;  r_s = r_n + (c_s h) v_n + h^2 sum_j abar_sj Ka_j
+// Stage state of stage S (1..6; 6 = the step's end point, row 6 of A = B), tableau pre-scaled by h (HTableau):
+//   v_s = v_n + sum_j (h a_sj) Ka_j ;  r_s = r_n + (c_s h) v_n + sum_j (h^2 abar_sj) Ka_j
+// Stages 1..5 accumulate straight onto the state (every fma has a constant-bank operand); the end point sums the
+// increment first and adds it once, as scipy's y_new = y + h (K^T b) does, so the carried state gets one rounding.
 // Ka_j lives in shared memory at Kt[(slot_j*3 + c)*BLOCK]; slot_0 = k0 (FSAL toggle), slot_j = j.
-template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state(const double *Kt, int k0, const double y[6], double h, double hh,
-                                            double ys[6]) {
-    double dv[3], dr[3];
-    {
-        const double *K0 = Kt + (k0 * K_ROWS) * BLOCK;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double k = K0[c * BLOCK];
-            dv[c] = c_T.a[S][0] * k;
-            dr[c] = (S >= 2) ? c_T.abar[S][0] * k : 0.0;
-        }
-    }
-#pragma unroll
-    for (int j = 1; j < S; ++j) {
-        const bool use_v = !(S == 6 && j == 1);  // B[1] = 0
-        const bool use_r = (j <= S - 2);          // abar[s][s-1] = 0
-        if (!use_v && !use_r) continue;
-        const double *Kj = Kt + (j * K_ROWS) * BLOCK;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const double k = Kj[c * BLOCK];
-            if (use_v) dv[c] = fma(c_T.a[S][j], k, dv[c]);
-            if (use_r) dr[c] = fma(c_T.abar[S][j], k, dr[c]);
-        }
-    }
-    const double ch = c_T.c[S] * h;
+// k_refine repeats exactly this arithmetic (stage_update below) when it recomputes the crossing step.
+template <int S>
+__device__ __forceinline__ void stage_update(const HTableau &ht, const double k[6][3], const double y[6], double ys[6]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        ys[3 + c] = fma(dv[c], h, y[3 + c]);
-        const double base = fma(ch, y[3 + c], y[c]);
-        ys[c] = (S >= 2) ? fma(dr[c], hh, base) : base;
+        const double base = fma(ht.ch[S], y[3 + c], y[c]);
+        if (S < 6) {
+            double v = y[3 + c], r = base;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v = fma(ht.ha[S][j], k[j][c], v);
+                if (j <= S - 2) r = fma(ht.hha[S][j], k[j][c], r);   // abar[s][s-1] = 0
+            }
+            ys[3 + c] = v; ys[c] = r;
+        } else {
+            double dv = ht.ha[6][0] * k[0][c], dr = ht.hha[6][0] * k[0][c];
+#pragma unroll
+            for (int j = 2; j < 6; ++j) dv = fma(ht.ha[6][j], k[j][c], dv);      // B[1] = 0
+#pragma unroll
+            for (int j = 1; j < 5; ++j) dr = fma(ht.hha[6][j], k[j][c], dr);
+            ys[3 + c] = y[3 + c] + dv; ys[c] = base + dr;
+        }
     }
+}
+
+template <int S, int BLOCK>
+__device__ __forceinline__ void stage_state(const double *Kt, int k0, const double y[6], const HTableau &ht,
+                                            double ys[6]) {
+    double k[6][3];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const double *Kj = Kt + ((j == 0 ? k0 : j) * K_ROWS) * BLOCK;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) k[j][c] = Kj[c * BLOCK];
+    }
+    stage_update<S>(ht, k, y, ys);
 }
 
 struct StepParams {
@@ -93,6 +98,7 @@ struct StepParams {
     int64_t run_step0;         // step index within the run of this launch's first step
     int64_t out_stride;
     double h;
+    HTableau ht;               // tableau scaled by h
     double event_altitude;
     // state / per-trajectory constants
     double *state;             // SoA [6][n]
@@ -248,8 +254,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     int k0 = 0;                     // slot currently holding Ka_0 (toggles 0 <-> 6, FSAL without a copy)
     int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));  // steps until the next stored sample
     int64_t next_k = p.run_step0 / p.out_stride + 1;
-    const double h = p.h, hh = p.h * p.h;
-
     for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
         const double *tile = tiles + (t % TILE_BUFFERS) * TILE_DOUBLES;
@@ -266,12 +270,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
 #pragma unroll
                         for (int c = 0; c < 6; ++c) ys[c] = y[c];
                         break;
-                    case 1: stage_state<1, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 2: stage_state<2, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 3: stage_state<3, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 4: stage_state<4, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 5: stage_state<5, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    default: stage_state<6, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    case 1: stage_state<1, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 2: stage_state<2, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 3: stage_state<3, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 4: stage_state<4, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 5: stage_state<5, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    default: stage_state<6, BLOCK>(Kt, k0, y, p.ht, ys); break;
                 }
                 const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
@@ -347,44 +351,19 @@ constexpr size_t propagate2_smem_bytes() {
 }
 
 template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state2(const double *Kt, int k0, const double y[2][6], double h, double hh,
+__device__ __forceinline__ void stage_state2(const double *Kt, int k0, const double y[2][6], const HTableau &ht,
                                              double ys[2][6]) {
-    double dv[2][3], dr[2][3];
-    {
-        const double *K0 = Kt + (k0 * K_ROWS) * 2 * BLOCK;
 #pragma unroll
-        for (int w = 0; w < 3; ++w)
+    for (int c = 0; c < 2; ++c) {       // the two trajectories of the pair
+        double k[6][3];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const double k = K0[(w * 2 + c) * BLOCK];
-                dv[c][w] = c_T.a[S][0] * k;
-                dr[c][w] = (S >= 2) ? c_T.abar[S][0] * k : 0.0;
-            }
-    }
+        for (int j = 0; j < S; ++j) {
+            const double *Kj = Kt + ((j == 0 ? k0 : j) * K_ROWS) * 2 * BLOCK;
 #pragma unroll
-    for (int j = 1; j < S; ++j) {
-        const bool use_v = !(S == 6 && j == 1);  // B[1] = 0
-        const bool use_r = (j <= S - 2);          // abar[s][s-1] = 0
-        if (!use_v && !use_r) continue;
-        const double *Kj = Kt + (j * K_ROWS) * 2 * BLOCK;
-#pragma unroll
-        for (int w = 0; w < 3; ++w)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const double k = Kj[(w * 2 + c) * BLOCK];
-                if (use_v) dv[c][w] = fma(c_T.a[S][j], k, dv[c][w]);
-                if (use_r) dr[c][w] = fma(c_T.abar[S][j], k, dr[c][w]);
-            }
-    }
-    const double ch = c_T.c[S] * h;
-#pragma unroll
-    for (int w = 0; w < 3; ++w)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            ys[c][3 + w] = fma(dv[c][w], h, y[c][3 + w]);
-            const double base = fma(ch, y[c][3 + w], y[c][w]);
-            ys[c][w] = (S >= 2) ? fma(dr[c][w], hh, base) : base;
+            for (int w = 0; w < 3; ++w) k[j][w] = Kj[(w * 2 + c) * BLOCK];
         }
+        stage_update<S>(ht, k, y[c], ys[c]);
+    }
 }
 
 template <int BLOCK, int MIN_BLOCKS>
@@ -464,8 +443,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate2(const StepPara
     int k0 = 0;
     int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));
     int64_t next_k = p.run_step0 / p.out_stride + 1;
-    const double h = p.h, hh = p.h * p.h;
-
     for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
         const double *tile = tiles + (t % TILE_BUFFERS) * TILE_DOUBLES;
@@ -482,12 +459,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate2(const StepPara
 #pragma unroll
                             for (int k = 0; k < 6; ++k) ys[c][k] = y[c][k];
                         break;
-                    case 1: stage_state2<1, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 2: stage_state2<2, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 3: stage_state2<3, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 4: stage_state2<4, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    case 5: stage_state2<5, BLOCK>(Kt, k0, y, h, hh, ys); break;
-                    default: stage_state2<6, BLOCK>(Kt, k0, y, h, hh, ys); break;
+                    case 1: stage_state2<1, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 2: stage_state2<2, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 3: stage_state2<3, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 4: stage_state2<4, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    case 5: stage_state2<5, BLOCK>(Kt, k0, y, p.ht, ys); break;
+                    default: stage_state2<6, BLOCK>(Kt, k0, y, p.ht, ys); break;
                 }
                 const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
@@ -647,6 +624,7 @@ struct RefineParams {
     const double *table;
     int64_t table_steps;
     double h, event_altitude;
+    HTableau ht;
     int skip_drag;
     double *state;  // in: y at the start of the crossing step; out: dense-output state at the impact time
     int64_t n;
@@ -736,17 +714,20 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
         double y[6], K[7][6], ys[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) y[c] = p.state[c * p.n + tid];
-        const double h = p.h, hh = p.h * p.h;
+        const double h = p.h;
 #pragma unroll 1
         for (int s = 0; s <= 6; ++s) {
-            for (int c = 0; c < 3; ++c) {
-                double dv = 0.0, dr = 0.0;
-                for (int j = 0; j < s; ++j) {
-                    dv = (j == 0) ? c_T.a[s][0] * K[0][3 + c] : fma(c_T.a[s][j], K[j][3 + c], dv);
-                    dr = (j == 0) ? c_T.abar[s][0] * K[0][3 + c] : fma(c_T.abar[s][j], K[j][3 + c], dr);
-                }
-                ys[3 + c] = (s == 0) ? y[3 + c] : fma(dv, h, y[3 + c]);
-                ys[c] = (s == 0) ? y[c] : fma(dr, hh, fma(c_T.c[s] * h, y[3 + c], y[c]));
+            double k[6][3];
+            for (int j = 0; j < 6; ++j)
+                for (int c = 0; c < 3; ++c) k[j][c] = (j < s) ? K[j][3 + c] : 0.0;
+            switch (s) {   // the step kernel's own stage arithmetic
+                case 0: for (int c = 0; c < 6; ++c) ys[c] = y[c]; break;
+                case 1: stage_update<1>(p.ht, k, y, ys); break;
+                case 2: stage_update<2>(p.ht, k, y, ys); break;
+                case 3: stage_update<3>(p.ht, k, y, ys); break;
+                case 4: stage_update<4>(p.ht, k, y, ys); break;
+                case 5: stage_update<5>(p.ht, k, y, ys); break;
+                default: stage_update<6>(p.ht, k, y, ys); break;
             }
             double a[3];
             if (p.skip_drag) acceleration<false, true>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);

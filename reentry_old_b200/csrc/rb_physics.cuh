@@ -454,4 +454,21 @@ constexpr Tableau make_tableau() {
     return t;
 }
 
+// The tableau pre-scaled by the (run-constant) step h, built once on the host and passed in the kernel
+// parameters (constant bank): stage updates become chains of fma(const, K, acc) with two register operands.
+struct HTableau {
+    double ha[7][6];    // h a_sj
+    double hha[7][6];   // h^2 abar_sj
+    double ch[7];       // c_s h
+};
+inline HTableau make_htableau(double h) {
+    const Tableau t = make_tableau();
+    HTableau o{};
+    for (int s = 0; s < 7; ++s) {
+        for (int j = 0; j < 6; ++j) { o.ha[s][j] = h * t.a[s][j]; o.hha[s][j] = (h * h) * t.abar[s][j]; }
+        o.ch[s] = t.c[s] * h;
+    }
+    return o;
+}
+
 }  // namespace rb
