@@ -32,7 +32,7 @@ enum : int {
 // (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
-    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r, tan_tol, rad2deg, latc;
+    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r, tan_tol, tan_tol_sure, rad2deg, latc;
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
@@ -54,7 +54,7 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
 #define RB_CONSTS_INIT                                                                              \
     {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
      RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
-     1.0 - RB_EARTH_E2 * RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 180.0 / RB_PI,           \
+     1.0 - RB_EARTH_E2 * RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 100.0 * 1.0000000000003333e-06, 180.0 / RB_PI,           \
      RB_LAT_FACTOR_COEF / 90.0, RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
      RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
@@ -140,8 +140,14 @@ RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, doubl
             for (int it = 1; it < RB_GEODETIC_MAX_ITER; ++it) {
                 const double q2 = rb_rsqrt(fma(B, B, g));
                 const double Bn2 = fma(-ke * B, q2, 1.0);
-                if (azp * fabs(Bn2 - B) < KC(tan_tol) * fma(B, Bn2, zp2)) break;
+                const double d = azp * fabs(Bn2 - B), S = fma(B, Bn2, zp2);
+                if (d < KC(tan_tol) * S) break;
                 B = Bn2;
+                // The iteration map B -> 1 - ke B / sqrt(B^2 + g) contracts by |f'| = ke g / (B^2 + g)^1.5
+                // <= 1.03 e2 R/|r| < 0.008 (|r| > 0.9 R, 0.99 < B < 1), and the right-hand side of the test
+                // shrinks by at most 0.98: d < 122 tol S here PROVES the next pass would break and return
+                // this Bn2 -- the pass that only confirms convergence is not computed (same returned iterate).
+                if (d < KC(tan_tol_sure) * S) break;
             }
         }
     }
