@@ -279,19 +279,17 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 }
                 const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
-                double a[3];
-                acceleration<false, SKIP>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
+                double a[3], alt_new;   // alt_new = |r_s| - R of the evaluated stage state
+                acceleration<false, SKIP>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr, &alt_new);
                 double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
                 Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
                 if (s == 6) {
-                    // step complete: ys = y_{n+1}
-                    const double r2n = fma(ys[2], ys[2], fma(ys[0], ys[0], ys[1] * ys[1]));
-                    const double alt_new = fma(r2n, rb_rsqrt(r2n), -KC(earth_r));   // |r| - R
+                    // step complete: ys = y_{n+1}; the event function is the altitude the FSAL evaluation just used
                     const double g_new = alt_new - p.event_altitude;
                     const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
-                    // non-finite detection on the exponent bits of |r|^2 (a NaN/Inf velocity reaches r one step
-                    // later; the FP64 pipe is the bottleneck, integer compares are free)
-                    const bool finite = (__double2hiint(r2n) & 0x7ff00000) != 0x7ff00000;
+                    // non-finite detection on the exponent bits of |r| - R (|r|^2 = inf or NaN makes it NaN; a
+                    // NaN/Inf velocity reaches r one step later; the FP64 pipe is the bottleneck, integer compares are free)
+                    const bool finite = (__double2hiint(alt_new) & 0x7ff00000) != 0x7ff00000;
                     if (!finite) {
                         alive = false;
                         p.status[tid] = RB_TRAJ_NONFINITE;

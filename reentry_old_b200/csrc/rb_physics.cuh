@@ -222,7 +222,7 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
 }
 template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
-                        double a[3], RhsOut *diag) {
+                        double a[3], RhsOut *diag, double *altitude_out = nullptr) {
     const double x = r[0], y = r[1], z = r[2];
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
@@ -270,6 +270,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
     // a = -(1/2 rho Cd A |v_rel|^2 / |v_rel|) v_rel / m = -(rho bc |v_rel|) v_rel
     const double altitude = fma(r2, ir, -KC(earth_r));   // |r| - R with |r| = r2 / sqrt(r2)  (:458)
+    if (altitude_out) *altitude_out = altitude;          // (the step kernel's event function reuses it)
     if (!SKIP || altitude <= RB_NEGLIGIBLE_DRAG_ALTITUDE_) {
         // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
         const double ip = rb_rsqrt(p2);
