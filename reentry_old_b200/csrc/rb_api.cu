@@ -46,7 +46,8 @@ struct rb_ctx {
     int device = 0;
     char err[512] = {0};
     // time table
-    double *d_table = nullptr;
+    double *d_table = nullptr;      // the step kernel's table (HOT_DOUBLES per entry)
+    double *d_table_abi = nullptr;  // the caller's table as uploaded (ENTRY_DOUBLES per entry), converted on the device
     int64_t table_capacity = 0;  // entries allocated
     int64_t table_steps = -1;    // steps covered
     double t0 = 0, dt = 0;
@@ -142,6 +143,7 @@ int32_t rb_ctx_destroy(rb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->d_table);
+    cudaFree(ctx->d_table_abi);
     cudaFree(ctx->d_live[0]);
     cudaFree(ctx->d_live[1]);
     cudaFree(ctx->d_block_counts);
@@ -207,13 +209,17 @@ int32_t rb_ctx_set_time_table(rb_ctx *ctx, const double *host_table, int64_t n_s
     if (n_entries > ctx->table_capacity) {
         CK(cudaStreamSynchronize((cudaStream_t)stream));
         cudaFree(ctx->d_table);
-        ctx->d_table = nullptr;
+        cudaFree(ctx->d_table_abi);
+        ctx->d_table = ctx->d_table_abi = nullptr;
         ctx->table_capacity = 0;
-        CK(cudaMalloc(&ctx->d_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_table, (size_t)n_entries * HOT_DOUBLES * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_table_abi, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double)));
         ctx->table_capacity = n_entries;
     }
-    CK(cudaMemcpyAsync(ctx->d_table, host_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double),
+    CK(cudaMemcpyAsync(ctx->d_table_abi, host_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double),
                        cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    k_hot_table<<<(unsigned)((n_entries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->d_table_abi, ctx->d_table, n_entries);
+    CK(cudaGetLastError());
     ctx->table_steps = n_steps;
     ctx->t0 = t0;
     ctx->dt = dt;

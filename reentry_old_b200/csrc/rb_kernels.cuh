@@ -39,7 +39,7 @@ namespace rb {
 constexpr int TILE_BUFFERS = RB_TILE_BUFFERS;  // 1 = single buffer (TMA latency exposed once per tile), 2 = double
 constexpr int TILE_STEPS = RB_TILE_STEPS;                                      // steps per time-table tile
 constexpr int TILE_ENTRIES = RB_STAGES_PER_STEP * TILE_STEPS + 1;  // 41 entries
-constexpr int TILE_DOUBLES = TILE_ENTRIES * ENTRY_DOUBLES;          // 656 doubles = 5248 B
+constexpr int TILE_DOUBLES = TILE_ENTRIES * HOT_DOUBLES;            // 492 doubles = 3936 B
 constexpr int K_SLOTS = 7;                                          // Ka_0..Ka_6 (acceleration rows only)
 constexpr int K_ROWS = 3;
 
@@ -53,7 +53,7 @@ __constant__ double c_P[7][4] = {RB_DP_P_ROWS};
 // Ka_j lives in shared memory at Kt[(slot_j*3 + c)*BLOCK]; slot_0 = k0 (FSAL toggle), slot_j = j.
 // k_refine repeats exactly this arithmetic (stage_update below) when it recomputes the crossing step.
 template <int S>
-__device__ __forceinline__ void stage_update(const HTableau &ht, const double k[6][3], const double y[6], double ys[6]) {
+RB_HD void stage_update(const HTableau &ht, const double k[6][3], const double y[6], double ys[6]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const double base = fma(ht.ch[S], y[3 + c], y[c]);
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     const int n_tiles = (p.n_launch_steps + TILE_STEPS - 1) / TILE_STEPS;
     auto tile_steps_of = [&](int t) { return min(TILE_STEPS, p.n_launch_steps - t * TILE_STEPS); };
     auto issue_tile = [&](int t) {  // thread 0 only
-        const uint32_t bytes = (uint32_t)((RB_STAGES_PER_STEP * tile_steps_of(t) + 1) * ENTRY_DOUBLES * sizeof(double));
-        const double *src = p.table + (RB_STAGES_PER_STEP * (p.table_step0 + (int64_t)t * TILE_STEPS)) * ENTRY_DOUBLES;
+        const uint32_t bytes = (uint32_t)((RB_STAGES_PER_STEP * tile_steps_of(t) + 1) * HOT_DOUBLES * sizeof(double));
+        const double *src = p.table + (RB_STAGES_PER_STEP * (p.table_step0 + (int64_t)t * TILE_STEPS)) * HOT_DOUBLES;
         uint64_t *bar = &bars[t % TILE_BUFFERS];
         mbar_expect_tx(bar, bytes);
         bulk_g2s(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES, src, bytes, bar);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
                 const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
                 double a[3], alt_new;   // alt_new = |r_s| - R of the evaluated stage state
-                acceleration<false, SKIP>(tile + e * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr, &alt_new);
+                acceleration<false, SKIP>(tile + e * HOT_DOUBLES, ys, ys + 3, body, a, nullptr, &alt_new);
                 double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
                 Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
                 if (s == 6) {
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate2(const StepPara
     const int n_tiles = (p.n_launch_steps + TILE_STEPS - 1) / TILE_STEPS;
     auto tile_steps_of = [&](int t) { return min(TILE_STEPS, p.n_launch_steps - t * TILE_STEPS); };
     auto issue_tile = [&](int t) {  // thread 0 only
-        const uint32_t bytes = (uint32_t)((RB_STAGES_PER_STEP * tile_steps_of(t) + 1) * ENTRY_DOUBLES * sizeof(double));
-        const double *src = p.table + (RB_STAGES_PER_STEP * (p.table_step0 + (int64_t)t * TILE_STEPS)) * ENTRY_DOUBLES;
+        const uint32_t bytes = (uint32_t)((RB_STAGES_PER_STEP * tile_steps_of(t) + 1) * HOT_DOUBLES * sizeof(double));
+        const double *src = p.table + (RB_STAGES_PER_STEP * (p.table_step0 + (int64_t)t * TILE_STEPS)) * HOT_DOUBLES;
         uint64_t *bar = &bars[t % TILE_BUFFERS];
         mbar_expect_tx(bar, bytes);
         bulk_g2s(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES, src, bytes, bar);
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate2(const StepPara
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { rr[c][k] = ys[c][k]; vv[c][k] = ys[c][3 + k]; }
-                acceleration2(tile + e * ENTRY_DOUBLES, rr, vv, body, a);
+                acceleration2(tile + e * HOT_DOUBLES, rr, vv, body, a);
                 double *Ksl = Kt + (slot_s * K_ROWS) * 2 * BLOCK;
 #pragma unroll
                 for (int w = 0; w < 3; ++w)
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
     // (an impact refined by an earlier chunk of a resumed run has a finite impact_time and is left alone)
     if (st == RB_TRAJ_IMPACTED && p.refine && p.impact_step && p.impact_time && p.impact_time[tid] != p.impact_time[tid]) {
         const int64_t n_abs = (int64_t)p.impact_step[tid] - 1;
-        const double *e0 = p.table + (RB_STAGES_PER_STEP * n_abs) * ENTRY_DOUBLES;
+        const double *e0 = p.table + (RB_STAGES_PER_STEP * n_abs) * HOT_DOUBLES;
         const Body body = make_body(p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s);
         double y[6], K[7][6], ys[6];
 #pragma unroll
@@ -728,8 +728,8 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
                 default: stage_update<6>(p.ht, k, y, ys); break;
             }
             double a[3];
-            if (p.skip_drag) acceleration<false, true>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
-            else acceleration<false, false>(e0 + ((s == 6) ? 5 : s) * ENTRY_DOUBLES, ys, ys + 3, body, a, nullptr);
+            if (p.skip_drag) acceleration<false, true>(e0 + ((s == 6) ? 5 : s) * HOT_DOUBLES, ys, ys + 3, body, a, nullptr);
+            else acceleration<false, false>(e0 + ((s == 6) ? 5 : s) * HOT_DOUBLES, ys, ys + 3, body, a, nullptr);
             K[s][0] = ys[3]; K[s][1] = ys[4]; K[s][2] = ys[5];
             K[s][3] = a[0];  K[s][4] = a[1];  K[s][5] = a[2];
         }
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
             }
             d.y_old[c] = y[c];
         }
-        d.t_old = e0[E_T];
+        d.t_old = e0[H_T];
         d.h = h;
         d.event_altitude = p.event_altitude;
         const double t_new = d.t_old + h;
@@ -1000,6 +1000,12 @@ __global__ void k_impact_points(int64_t n, const double *final_state, const doub
 // norm, SAFETY 0.9, factor clamp 0.2..10, no growth after a rejection, min step 10 ulp), events and t_eval
 // sampling on the quartic dense output (ivp.py:659-733).  Time-dependent inputs (Sun/Moon ephemeris, solar
 // factor) are evaluated at every stage time on the device (time_entry), since no two lanes share a time grid.
+// ABI table (16 doubles / entry) -> the step kernel's 96-byte entries (rb_ctx_set_time_table)
+__global__ void k_hot_table(const double *__restrict__ abi, double *__restrict__ hot, int64_t n_entries) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_entries) hot_entry(abi + i * ENTRY_DOUBLES, hot + i * HOT_DOUBLES);
+}
+
 struct AdaptiveParams {
     int64_t n;
     const double *y0;
@@ -1030,9 +1036,11 @@ __global__ void __launch_bounds__(64) k_adaptive(const AdaptiveParams p) {
     const Body body = make_body(p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s);
     double y[6], f[6], K[7][6], ynew[6], fnew[6], ent[ENTRY_DOUBLES];
     auto rhs = [&](double t, const double *yy, double *dy) {
+        double hot[HOT_DOUBLES];
         time_entry(t, p.epoch_jd, p.gmst0, ent);
+        hot_entry(ent, hot);
         double a[3];
-        acceleration<false>(ent, yy, yy + 3, body, a, nullptr);
+        acceleration<false>(hot, yy, yy + 3, body, a, nullptr);
         dy[0] = yy[3]; dy[1] = yy[4]; dy[2] = yy[5]; dy[3] = a[0]; dy[4] = a[1]; dy[5] = a[2];
     };
 #pragma unroll

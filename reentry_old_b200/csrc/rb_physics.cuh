@@ -21,11 +21,25 @@ namespace rb {
 
 constexpr double RB_NEGLIGIBLE_DRAG_ALTITUDE_ = 400000.0;  // == RB_NEGLIGIBLE_DRAG_ALTITUDE of the C ABI
 
-// time-table entry layout (include/reentry_b200.h)
+// time-table entry layout of the C ABI (include/reentry_b200.h): what rb_build_time_table writes
 enum : int {
     E_SUN = 0, E_MOON = 3, E_SUN_IND = 6, E_MOON_IND = 9, E_CG = 12, E_SG = 13, E_SOLAR = 14, E_T = 15,
     ENTRY_DOUBLES = 16
 };
+// ... and the 96-byte form the step kernel streams through shared memory (rb_ctx_set_time_table converts on the
+// device): only what the hot RHS reads, with the two time-only indirect third-body terms pre-summed and negated
+// so that they ride on the gravity multiply (a = k r - ind, one DFMA per component).
+enum : int { H_SUN = 0, H_MOON = 3, H_NIND = 6, H_SOLAR = 9, H_T = 10, HOT_DOUBLES = 12 };
+RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
+    for (int c = 0; c < 3; ++c) {
+        h[H_SUN + c] = e[E_SUN + c];
+        h[H_MOON + c] = e[E_MOON + c];
+        h[H_NIND + c] = -(e[E_MOON_IND + c] + e[E_SUN_IND + c]);
+    }
+    h[H_SOLAR] = e[E_SOLAR];
+    h[H_T] = e[E_T];
+    h[11] = 0.0;
+}
 
 // ---- constants of the hot RHS, kept in the constant bank ---------------------------------
 // A 64-bit literal that is not a 32-bit-encodable immediate costs two UMOVs per use on sm_100
@@ -220,6 +234,8 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
     T_out = T;
     return P * latitude_factor * rb_rcp(KC(rgas) * T) * factor;
 }
+// `e` is a HOT entry (H_*) for the integrators (DIAG = false) and an ABI entry (E_*) for the diagnostics
+// (DIAG = true), which report the third-body terms of the two bodies separately as the reference does.
 template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
                         double a[3], RhsOut *diag, double *altitude_out = nullptr) {
@@ -244,27 +260,42 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         ax = diag->a_grav[0] + diag->a_j2[0]; ay = diag->a_grav[1] + diag->a_j2[1]; az = diag->a_grav[2] + diag->a_j2[2];
     } else {
         const double kxy = gk + fxy;
-        ax = kxy * x; ay = kxy * y; az = (gk + fz) * z;
+        ax = fma(kxy, x, e[H_NIND + 0]); ay = fma(kxy, y, e[H_NIND + 1]); az = fma(gk + fz, z, e[H_NIND + 2]);
     }
     // third bodies as a lambda: evaluated inside the drag block (fills the latency of its serial tail)
     // or on their own when the drag block is skipped
     auto third_bodies = [&]() {
         // third bodies, :355-363 : k d/|d|^3 - k s/|s|^3 (the second term is time-only -> table)
-        {
-            const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
-            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-            const double k3 = KC(moon_k) * (id * id * id);
-            const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
-            ax += mx; ay += my; az += mz;
-            if (DIAG) { diag->a_moon[0] = mx; diag->a_moon[1] = my; diag->a_moon[2] = mz; }
-        }
-        {
-            const double dx = e[E_SUN + 0] - x, dy = e[E_SUN + 1] - y, dz = e[E_SUN + 2] - z;
-            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-            const double k3 = KC(sun_k) * (id * id * id);
-            const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
-            ax += sx; ay += sy; az += sz;
-            if (DIAG) { diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz; }
+        if (DIAG) {
+            {
+                const double dx = e[E_MOON + 0] - x, dy = e[E_MOON + 1] - y, dz = e[E_MOON + 2] - z;
+                const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double k3 = KC(moon_k) * (id * id * id);
+                const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
+                ax += mx; ay += my; az += mz;
+                diag->a_moon[0] = mx; diag->a_moon[1] = my; diag->a_moon[2] = mz;
+            }
+            {
+                const double dx = e[E_SUN + 0] - x, dy = e[E_SUN + 1] - y, dz = e[E_SUN + 2] - z;
+                const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double k3 = KC(sun_k) * (id * id * id);
+                const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
+                ax += sx; ay += sy; az += sz;
+                diag->a_sun[0] = sx; diag->a_sun[1] = sy; diag->a_sun[2] = sz;
+            }
+        } else {   // the indirect terms are already in (ax, ay, az): accumulate the direct ones
+            {
+                const double dx = e[H_MOON + 0] - x, dy = e[H_MOON + 1] - y, dz = e[H_MOON + 2] - z;
+                const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double k3 = KC(moon_k) * (id * id * id);
+                ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
+            }
+            {
+                const double dx = e[H_SUN + 0] - x, dy = e[H_SUN + 1] - y, dz = e[H_SUN + 2] - z;
+                const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double k3 = KC(sun_k) * (id * id * id);
+                ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
+            }
         }
     };
     // drag, :458-465 : spherical altitude, geodetic latitude (deg), density,
@@ -279,7 +310,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         third_bodies();
         const double lat_deg = pair_abs_latitude_deg(gA, gB);
         double T;
-        const double rho = density(altitude, lat_deg, e[E_SOLAR], T);
+        const double rho = density(altitude, lat_deg, e[DIAG ? (int)E_SOLAR : (int)H_SOLAR], T);
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
         const double vn = w2 * rb_rsqrt(w2);
         const double kd = -(rho * b.bc) * vn;
@@ -330,7 +361,7 @@ RB_HD void acceleration2(const double *__restrict__ e, const double r[2][3], con
         const double q = (5.0 * ir2) * (z[c] * z[c]);
         const double fxy = fma(q, f, -f), fz = fma(q, f, -3.0 * f);
         const double kxy = gk + fxy;
-        ax[c] = kxy * x[c]; ay[c] = kxy * y[c]; az[c] = (gk + fz) * z[c];
+        ax[c] = fma(kxy, x[c], e[H_NIND + 0]); ay[c] = fma(kxy, y[c], e[H_NIND + 1]); az[c] = fma(gk + fz, z[c], e[H_NIND + 2]);
         altitude[c] = fma(r2[c], ir[c], -KC(earth_r));
     }
     // geodetic pair iteration (geodetic_pair), merged over the two trajectories
@@ -372,18 +403,16 @@ RB_HD void acceleration2(const double *__restrict__ e, const double r[2][3], con
     // third bodies (fill the latency of the serial latitude -> density -> drag tail)
     RB_PAIR {
         {
-            const double dx = e[E_MOON + 0] - x[c], dy = e[E_MOON + 1] - y[c], dz = e[E_MOON + 2] - z[c];
+            const double dx = e[H_MOON + 0] - x[c], dy = e[H_MOON + 1] - y[c], dz = e[H_MOON + 2] - z[c];
             const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
             const double k3 = KC(moon_k) * (id * id * id);
-            const double mx = fma(k3, dx, -e[E_MOON_IND + 0]), my = fma(k3, dy, -e[E_MOON_IND + 1]), mz = fma(k3, dz, -e[E_MOON_IND + 2]);
-            ax[c] += mx; ay[c] += my; az[c] += mz;
+            ax[c] = fma(k3, dx, ax[c]); ay[c] = fma(k3, dy, ay[c]); az[c] = fma(k3, dz, az[c]);
         }
         {
-            const double dx = e[E_SUN + 0] - x[c], dy = e[E_SUN + 1] - y[c], dz = e[E_SUN + 2] - z[c];
+            const double dx = e[H_SUN + 0] - x[c], dy = e[H_SUN + 1] - y[c], dz = e[H_SUN + 2] - z[c];
             const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
             const double k3 = KC(sun_k) * (id * id * id);
-            const double sx = fma(k3, dx, -e[E_SUN_IND + 0]), sy = fma(k3, dy, -e[E_SUN_IND + 1]), sz = fma(k3, dz, -e[E_SUN_IND + 2]);
-            ax[c] += sx; ay[c] += sy; az[c] += sz;
+            ax[c] = fma(k3, dx, ax[c]); ay[c] = fma(k3, dy, ay[c]); az[c] = fma(k3, dz, az[c]);
         }
     }
     double lat_deg[2], rho[2];
@@ -392,11 +421,11 @@ RB_HD void acceleration2(const double *__restrict__ e, const double r[2][3], con
         // both in the top layer above the solar-factor blend: the common branch of density(), pairwise
         RB_PAIR {
             const double latitude_factor = fma(KC(latc), lat_deg[c], 1.0);
-            rho[c] = (KC(top_rho0) * rb_exp((altitude[c] - KC(top_h)) * KC(top_k))) * (latitude_factor * e[E_SOLAR]);
+            rho[c] = (KC(top_rho0) * rb_exp((altitude[c] - KC(top_h)) * KC(top_k))) * (latitude_factor * e[H_SOLAR]);
         }
     } else {
         double T;
-        RB_PAIR rho[c] = density(altitude[c], lat_deg[c], e[E_SOLAR], T);
+        RB_PAIR rho[c] = density(altitude[c], lat_deg[c], e[H_SOLAR], T);
     }
     RB_PAIR {
         const double w2 = fma(wz[c], wz[c], fma(wx[c], wx[c], wy[c] * wy[c]));

@@ -38,33 +38,31 @@ double hh_density(double alt, double lat, double solar_time, double *T) { return
 // one trajectory.  table: [(5*n_steps+1)][16].  ys_out: [n_steps+1][6].  Returns the impact step or -1.
 int64_t hh_propagate(const double *table, const double *y0, double cd, double area, double mass, double h,
                      int64_t n_steps, double event_altitude, double *ys_out) {
-    static const Tableau T = make_tableau();
+    const HTableau ht = make_htableau(h);
     const Body b = make_body(cd, area, mass);
     double y[6], Ka[7][3], ys[6];
     memcpy(y, y0, sizeof y);
     memcpy(ys_out, y, sizeof y);
     double g_old = event_g(y, event_altitude);
-    const double hh = h * h;
     int k0 = 0;
     for (int64_t n = 0; n < n_steps; ++n) {
         for (int s = (n == 0 ? 0 : 1); s <= 6; ++s) {
             const int slot = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
-            if (s == 0) memcpy(ys, y, sizeof y);
-            else {
-                for (int c = 0; c < 3; ++c) {
-                    double dv = T.a[s][0] * Ka[k0][c];
-                    double dr = (s >= 2) ? T.abar[s][0] * Ka[k0][c] : 0.0;
-                    for (int j = 1; j < s; ++j) {
-                        if (T.a[s][j] != 0.0) dv = fma(T.a[s][j], Ka[j][c], dv);
-                        if (T.abar[s][j] != 0.0) dr = fma(T.abar[s][j], Ka[j][c], dr);
-                    }
-                    ys[3 + c] = fma(dv, h, y[3 + c]);
-                    const double base = fma(T.c[s] * h, y[3 + c], y[c]);
-                    ys[c] = (s >= 2) ? fma(dr, hh, base) : base;
-                }
+            double k[6][3];
+            for (int j = 0; j < 6; ++j) memcpy(k[j], Ka[j == 0 ? k0 : j], sizeof k[j]);
+            switch (s) {
+                case 0: memcpy(ys, y, sizeof y); break;
+                case 1: stage_update<1>(ht, k, y, ys); break;
+                case 2: stage_update<2>(ht, k, y, ys); break;
+                case 3: stage_update<3>(ht, k, y, ys); break;
+                case 4: stage_update<4>(ht, k, y, ys); break;
+                case 5: stage_update<5>(ht, k, y, ys); break;
+                default: stage_update<6>(ht, k, y, ys); break;
             }
             const int64_t e = 5 * n + ((s == 6) ? 5 : s);
-            acceleration<false>(table + e * 16, ys, ys + 3, b, Ka[slot], nullptr);
+            double hot[HOT_DOUBLES];
+            hot_entry(table + e * 16, hot);
+            acceleration<false>(hot, ys, ys + 3, b, Ka[slot], nullptr);
         }
         const double g_new = event_g(ys, event_altitude);
         if (g_old >= 0.0 && g_new <= 0.0) return n + 1;
