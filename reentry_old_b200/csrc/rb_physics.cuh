@@ -211,9 +211,7 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
     if (altitude < KC(blend_alt)) {
-        double ep, es;
-        rb_exp_parts(-KC(sig_ks) * (altitude - KC(sig_x0)), ep, es);
-        const double normalized = rb_rcp(fma(ep, es, 1.0));   // 1 / (1 + e^(-k (x - x0)))
+        const double normalized = rb_rcp(1.0 + rb_exp(-KC(sig_ks) * (altitude - KC(sig_x0))));   // 1 / (1 + e^(-k (x - x0)))
         factor = fma(factor - 1.0, normalized, 1.0);
     }
     const double latitude_factor = fma(KC(latc), abs_latitude_deg, 1.0);
