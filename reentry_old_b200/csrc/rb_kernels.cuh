@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         // s = 0 only for the very first evaluation of the launch (Ka_0 = a(t_n, y_n)).
         int m = 0;
         int s = (t == 0) ? 0 : 1;
+        const double *ent = tile + s * HOT_DOUBLES;   // entry 5 m + min(s, 5) of the tile, advanced with the stage
         while (m < ts) {
             if (alive) {
                 double ys[6];
@@ -277,10 +278,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                     case 5: stage_state<5, BLOCK>(Kt, k0, y, p.ht, ys); break;
                     default: stage_state<6, BLOCK>(Kt, k0, y, p.ht, ys); break;
                 }
-                const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
-                const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
+                const int slot_s = (s == 6) ? (6 - k0) : s;   // (s == 0 happens only while k0 == 0)
                 double a[3], alt_new;   // alt_new = |r_s| - R of the evaluated stage state
-                acceleration<false, SKIP>(tile + e * HOT_DOUBLES, ys, ys + 3, body, a, nullptr, &alt_new);
+                acceleration<false, SKIP>(ent, ys, ys + 3, body, a, nullptr, &alt_new);
                 double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
                 Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
                 if (s == 6) {
@@ -317,12 +317,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 k0 = 6 - k0;
                 ++m;
                 s = 1;
+                ent += HOT_DOUBLES;
                 if (--to_sample == 0) { to_sample = (int)p.out_stride; ++next_k; }
                 // warp-ballot retirement: a warp with no live lane leaves (warp 0 stays while
                 // tiles remain to be issued)
                 if (!__any_sync(0xffffffffu, alive) && (threadIdx.x >= 32 || t + TILE_BUFFERS >= n_tiles)) goto done;
             } else {
                 ++s;
+                if (s != 6) ent += HOT_DOUBLES;   // stage 6 is evaluated at t_{n+1}, the entry of stage 5
             }
         }
         if (t + TILE_BUFFERS < n_tiles) {
