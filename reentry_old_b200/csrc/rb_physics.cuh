@@ -215,25 +215,28 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
         factor = fma(factor - 1.0, normalized, 1.0);
     }
     const double latitude_factor = fma(KC(latc), abs_latitude_deg, 1.0);
+    // rho = c0 e^arg (latitude_factor factor): every layer funnels into ONE exp, so that a warp whose lanes sit in
+    // different layers (isothermal / gradient / top) does not execute one exponential per layer kind
+    double arg, c0, T;
     if (altitude >= KC(top_h)) {  // top layer (i == 7): isothermal + the extra scale-height tail
-        T_out = KC(top_T);        // P7 / (R_GAS T7) is a constant of the layer
-        return (KC(top_rho0) * rb_exp((altitude - KC(top_h)) * KC(top_k))) * (latitude_factor * factor);
+        T = KC(top_T);            // P7 / (R_GAS T7) is a constant of the layer
+        arg = (altitude - KC(top_h)) * KC(top_k);
+        c0 = KC(top_rho0);
+    } else {
+        // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
+        int i = (altitude >= KC(bp[4])) ? 4 : 0;
+        i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
+        i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
+        const double dh = altitude - KC(bp[i]);
+        const double L = KC(gr[i]);
+        T = fma(L, dh, KC(bt[i]));
+        arg = dh * KC(iso_k[i]);                                                   // isothermal: P_i e^(k dh), :84
+        if (L != 0.0) arg = KC(pow_k[i]) * rb_log_near1(T * KC(inv_bt[i]));        // gradient: P_i (T/T_i)^k, :86
+        c0 = KC(bpz[i]) * rb_rcp(KC(rgas) * T);                                    // P / (R_GAS T), :88
     }
-    // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
-    int i = (altitude >= KC(bp[4])) ? 4 : 0;
-    i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
-    i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
-    const double dh = altitude - KC(bp[i]);
-    const double L = KC(gr[i]);
-    const double T = fma(L, dh, KC(bt[i]));
-    double P;
-    if (L == 0.0) P = KC(bpz[i]) * rb_exp(dh * KC(iso_k[i]));
-    else P = KC(bpz[i]) * rb_pow_near1(T * KC(inv_bt[i]), KC(pow_k[i]));
     T_out = T;
-    return P * latitude_factor * rb_rcp(KC(rgas) * T) * factor;
+    return (c0 * rb_exp(arg)) * (latitude_factor * factor);
 }
-// `e` is a HOT entry (H_*) for the integrators (DIAG = false) and an ABI entry (E_*) for the diagnostics
-// (DIAG = true), which report the third-body terms of the two bodies separately as the reference does.
 template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
                         double a[3], RhsOut *diag, double *altitude_out = nullptr) {
