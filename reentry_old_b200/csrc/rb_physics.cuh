@@ -52,6 +52,10 @@ struct Consts {
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
     double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
     double inv_bt[RB_N_LAYERS];  // 1 / T_i
+    // the same per-layer constants packed for the hot path: one 64-byte record per layer (three LDC.128 instead of
+    // nine LDC.64 with a lane-dependent index): {h_i, L_i}, {T_i, L_i / T_i}, {k_i, P_i} with k_i = gM/(R* T_i) on
+    // isothermal layers and gM/(R* L_i) on gradient layers
+    double layer[RB_N_LAYERS][8];
 };
 
 #define RB_GM_ (-RB_EARTH_GRAVITY * RB_AIR_MOLAR_MASS)
@@ -64,6 +68,8 @@ constexpr double rb_isok_(int i) { return RB_GM_ / (RB_GAS_CONSTANT * rb_bt_(i))
 constexpr double rb_powk_(int i) { return rb_gr_(i) == 0.0 ? 0.0 : RB_GM_ / (RB_GAS_CONSTANT * rb_gr_(i)); }
 #define RB_L8_(f) {f(0), f(1), f(2), f(3), f(4), f(5), f(6), f(7)}
 constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
+#define RB_LAYER_(i) {rb_bp_(i), rb_gr_(i), rb_bt_(i), rb_gr_(i) / rb_bt_(i),                         \
+                      rb_gr_(i) == 0.0 ? rb_isok_(i) : rb_powk_(i), rb_bpz_(i), 0.0, 0.0}
 
 #define RB_CONSTS_INIT                                                                              \
     {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
@@ -73,7 +79,7 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
      RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
-     RB_L8_(rb_powk_), RB_L8_(rb_invbt_)}
+     RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_)}
 
 #if defined(__CUDACC__)
 __constant__ Consts c_k = RB_CONSTS_INIT;
@@ -227,12 +233,14 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
         int i = (altitude >= KC(bp[4])) ? 4 : 0;
         i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
         i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
-        const double dh = altitude - KC(bp[i]);
-        const double L = KC(gr[i]);
-        T = fma(L, dh, KC(bt[i]));
-        arg = dh * KC(iso_k[i]);                                                   // isothermal: P_i e^(k dh), :84
-        if (L != 0.0) arg = KC(pow_k[i]) * rb_log_near1(T * KC(inv_bt[i]));        // gradient: P_i (T/T_i)^k, :86
-        c0 = KC(bpz[i]) * rb_rcp(KC(rgas) * T);                                    // P / (R_GAS T), :88
+        const double *__restrict__ lay = KC(layer[i]);
+        const double dh = altitude - lay[0];
+        const double L = lay[1];
+        T = fma(L, dh, lay[2]);
+        const double k = lay[4];
+        arg = dh * k;                                                   // isothermal: P_i e^(k dh), :84
+        if (L != 0.0) arg = k * rb_log1p_small(lay[3] * dh);            // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
+        c0 = lay[5] * rb_rcp(KC(rgas) * T);                             // P / (R_GAS T), :88
     }
     T_out = T;
     return (c0 * rb_exp(arg)) * (latitude_factor * factor);
