@@ -71,8 +71,6 @@ typedef enum rb_traj_status {
                                    ordered after prior work on `stream` and joined back before the call's last
                                    kernel, so the caller still sees ONE stream) */
 #define RB_OVERLAP_MIN_TRAJECTORIES 600000
-#define RB_FLAG_PAIRWISE_KERNEL 128u /* use the two-trajectories-per-thread step kernel while a partition has >= 200k
-                                   live trajectories (bit-identical results; off by default: not faster on B200) */
 #define RB_FLAG_RESUME 256u       /* checkpoint / resume: continue a run whose previous chunk ended at table step
                                    `first_step` (a multiple of out_stride).  in->y0 is ignored; out->final_state,
                                    status, impact_step, impact_time (and samples, indexed by the absolute step) are the

@@ -28,20 +28,6 @@ using namespace rb;
 #ifndef RB_MIN_BLOCKS
 #define RB_MIN_BLOCKS 6
 #endif
-// Pairwise kernel (two trajectories per thread; opt-in, RB_FLAG_PAIRWISE_KERNEL): launch shape and the live count
-// above which it is used.  Measured on C2 (1 M): 128x3 6.56, 128x4 7.16, 256x2 7.12, 64x8 6.74 G traj-steps/s vs 7.54 for the
-// one-trajectory kernel -- 11 % fewer instructions per trajectory-step, but the FP64 pipe stays at 68 % and the
-// coarser blocks (256 trajectories) quantise the waves of a 1 M ensemble worse.
-#ifndef RB_BLOCK2
-#define RB_BLOCK2 128
-#endif
-#ifndef RB_MIN_BLOCKS2
-#define RB_MIN_BLOCKS2 4
-#endif
-#ifndef RB_PAIR_MIN_LIVE
-#define RB_PAIR_MIN_LIVE 200000
-#endif
-
 struct rb_ctx {
     int device = 0;
     char err[512] = {0};
@@ -125,9 +111,6 @@ int32_t rb_ctx_create(rb_ctx **out, int32_t device) {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)propagate_smem_bytes<RB_BLOCK>());
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_propagate2<RB_BLOCK2, RB_MIN_BLOCKS2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)propagate2_smem_bytes<RB_BLOCK2>());
     }
     if (e != cudaSuccess) {
         fprintf(stderr, "rb_ctx_create: %s\n", cudaGetErrorString(e));
@@ -340,7 +323,6 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     const bool early = (run->flags & RB_FLAG_EARLY_EXIT) != 0;
     const bool profile = (run->flags & RB_FLAG_PROFILE) != 0;
     const bool skip_drag = (run->flags & RB_FLAG_SKIP_NEGLIGIBLE_DRAG) != 0;
-    const bool use_pairs = (run->flags & RB_FLAG_PAIRWISE_KERNEL) != 0;
 
     // partitions: two when each half still fills the machine several times over
     const int n_parts = (n >= RB_OVERLAP_MIN_TRAJECTORIES && !(run->flags & RB_FLAG_NO_OVERLAP)) ? 2 : 1;
@@ -416,10 +398,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             sp.n_live = pt.n_live;
             const unsigned grid = (unsigned)((pt.live_bound + RB_BLOCK - 1) / RB_BLOCK);
             if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
-            else if (use_pairs && pt.live_bound >= RB_PAIR_MIN_LIVE) {
-                const unsigned grid2 = (unsigned)(((pt.live_bound + 1) / 2 + RB_BLOCK2 - 1) / RB_BLOCK2);
-                k_propagate2<RB_BLOCK2, RB_MIN_BLOCKS2><<<grid2, RB_BLOCK2, propagate2_smem_bytes<RB_BLOCK2>(), pt.s>>>(sp);
-            } else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
+            else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
             ctx->stats.propagate_launches++;

@@ -8,7 +8,6 @@
 //                     that 80 registers buy 24 resident warps; warp-vote retirement of impacted lanes;
 //                     SoA streaming stores of the decimated samples (to HBM or straight to pinned host
 //                     memory).  Template bool SKIP = RB_FLAG_SKIP_NEGLIGIBLE_DRAG instantiation.
-//   k_propagate2      the same arithmetic for two trajectories per thread (opt-in experiment)
 //   k_count_live / k_scan_blocks / k_scatter_live
 //                     order-preserving compaction of the live-trajectory index list
 //   k_refine          impact-time refinement on the step's quartic dense output (Brent), n_samples
@@ -337,204 +336,6 @@ done:
 #pragma unroll
         for (int c = 0; c < 6; ++c) p.state[c * p.n + tid] = y[c];
     }
-}
-
-// ---------------------------------------------------------------- the hot kernel, two trajectories per thread
-// Same step arithmetic as k_propagate (bit-identical results), with the statements of a PAIR of
-// trajectories adjacent so that the FP64 pipe sees back-to-back independent instructions from the same
-// warp (acceleration2 in rb_physics.cuh).  Thread i owns live-list entries 2i and 2i+1; a member that is
-// missing / already retired mirrors its partner's state so that the merged geodetic loop never waits on it.
-// Ka of slot s, row w, member c at Kt[((s*3 + w)*2 + c)*BLOCK].
-template <int BLOCK>
-constexpr size_t propagate2_smem_bytes() {
-    return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + 2 * K_SLOTS * K_ROWS * BLOCK) + 2 * sizeof(uint64_t);
-}
-
-template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state2(const double *Kt, int k0, const double y[2][6], const HTableau &ht,
-                                             double ys[2][6]) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {       // the two trajectories of the pair
-        double k[6][3];
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            const double *Kj = Kt + ((j == 0 ? k0 : j) * K_ROWS) * 2 * BLOCK;
-#pragma unroll
-            for (int w = 0; w < 3; ++w) k[j][w] = Kj[(w * 2 + c) * BLOCK];
-        }
-        stage_update<S>(ht, k, y[c], ys[c]);
-    }
-}
-
-template <int BLOCK, int MIN_BLOCKS>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate2(const StepParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *tiles = reinterpret_cast<double *>(smem_raw);
-    double *Ks = tiles + TILE_BUFFERS * TILE_DOUBLES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Ks + 2 * K_SLOTS * K_ROWS * BLOCK);
-
-    const int n_live = *p.n_live;
-    const int64_t i0 = (int64_t)blockIdx.x * BLOCK;   // pair index of this block's first thread
-    if (2 * i0 >= n_live) return;
-    const int64_t ip = i0 + threadIdx.x;
-
-    const int n_tiles = (p.n_launch_steps + TILE_STEPS - 1) / TILE_STEPS;
-    auto tile_steps_of = [&](int t) { return min(TILE_STEPS, p.n_launch_steps - t * TILE_STEPS); };
-    auto issue_tile = [&](int t) {  // thread 0 only
-        const uint32_t bytes = (uint32_t)((RB_STAGES_PER_STEP * tile_steps_of(t) + 1) * HOT_DOUBLES * sizeof(double));
-        const double *src = p.table + (RB_STAGES_PER_STEP * (p.table_step0 + (int64_t)t * TILE_STEPS)) * HOT_DOUBLES;
-        uint64_t *bar = &bars[t % TILE_BUFFERS];
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES, src, bytes, bar);
-    };
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_barrier_init();
-        fence_proxy_async();
-        issue_tile(0);
-        if (TILE_BUFFERS > 1 && n_tiles > 1) issue_tile(1);
-    }
-
-    int32_t tid[2] = {0, 0};
-    bool alive[2], loaded[2];
-    double y[2][6];
-    Body body[2];
-    double g_old[2];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const int64_t li = 2 * ip + c;
-        alive[c] = li < n_live;
-        if (alive[c]) {
-            tid[c] = p.live[li];
-            alive[c] = p.status[tid[c]] == RB_TRAJ_ALIVE;
-        }
-        loaded[c] = alive[c];
-        double b_cd = p.cd_s, b_area = p.area_s, b_mass = p.mass_s;
-        if (alive[c]) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) y[c][k] = p.state[k * p.n + tid[c]];
-            if (p.cd) b_cd = p.cd[tid[c]];
-            if (p.area) b_area = p.area[tid[c]];
-            if (p.mass) b_mass = p.mass[tid[c]];
-        }
-        body[c] = make_body(b_cd, b_area, b_mass);
-    }
-    // a missing member mirrors its partner (finite state, same geodetic iteration count)
-    if (!alive[0] && alive[1]) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) y[0][k] = y[1][k];
-        body[0] = body[1];
-    }
-    if (!alive[1]) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) y[1][k] = alive[0] ? y[0][k] : 1.0;
-        body[1] = body[0];
-    }
-    if (!alive[0] && !alive[1]) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) y[0][k] = 1.0;
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) g_old[c] = event_g(y[c], p.event_altitude);
-    __syncthreads();  // barrier init visible to all before anyone waits
-
-    double *Kt = Ks + threadIdx.x;
-    int k0 = 0;
-    int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));
-    int64_t next_k = p.run_step0 / p.out_stride + 1;
-    for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
-        const double *tile = tiles + (t % TILE_BUFFERS) * TILE_DOUBLES;
-        const int ts = tile_steps_of(t);
-        int m = 0;
-        int s = (t == 0) ? 0 : 1;
-        while (m < ts) {
-            if (alive[0] || alive[1]) {
-                double ys[2][6];
-                switch (s) {
-                    case 0:
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-#pragma unroll
-                            for (int k = 0; k < 6; ++k) ys[c][k] = y[c][k];
-                        break;
-                    case 1: stage_state2<1, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 2: stage_state2<2, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 3: stage_state2<3, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 4: stage_state2<4, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 5: stage_state2<5, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    default: stage_state2<6, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                }
-                const int slot_s = (s == 0) ? k0 : ((s == 6) ? (6 - k0) : s);
-                const int e = RB_STAGES_PER_STEP * m + ((s == 6) ? 5 : s);
-                double a[2][3], rr[2][3], vv[2][3];
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { rr[c][k] = ys[c][k]; vv[c][k] = ys[c][3 + k]; }
-                acceleration2(tile + e * HOT_DOUBLES, rr, vv, body, a);
-                double *Ksl = Kt + (slot_s * K_ROWS) * 2 * BLOCK;
-#pragma unroll
-                for (int w = 0; w < 3; ++w)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) Ksl[(w * 2 + c) * BLOCK] = a[c][w];
-                if (s == 6) {
-                    const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const double r2n = fma(ys[c][2], ys[c][2], fma(ys[c][0], ys[c][0], ys[c][1] * ys[c][1]));
-                        const double alt_new = fma(r2n, rb_rsqrt(r2n), -KC(earth_r));
-                        const double g_new = alt_new - p.event_altitude;
-                        const bool finite = (__double2hiint(r2n) & 0x7ff00000) != 0x7ff00000;
-                        if (alive[c]) {
-                            if (!finite) {
-                                alive[c] = false;
-                                p.status[tid[c]] = RB_TRAJ_NONFINITE;
-                                if (p.impact_step) p.impact_step[tid[c]] = (int32_t)step_abs;
-                            } else if (g_old[c] >= 0.0 && g_new <= 0.0) {
-                                alive[c] = false;
-                                p.status[tid[c]] = RB_TRAJ_IMPACTED;
-                                if (p.impact_step) p.impact_step[tid[c]] = (int32_t)step_abs;
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 6; ++k) y[c][k] = ys[c][k];
-                                g_old[c] = g_new;
-                                if (to_sample == 1 && p.samples) {
-                                    double *sp = p.samples + next_k * p.sample_stride + tid[c];
-#pragma unroll
-                                    for (int k = 0; k < 6; ++k) st_stream(sp + k * p.field_stride, ys[c][k]);
-                                    st_stream(sp + 6 * p.field_stride, alt_new);
-                                    const double v2 = fma(ys[c][5], ys[c][5], fma(ys[c][3], ys[c][3], ys[c][4] * ys[c][4]));
-                                    st_stream(sp + 7 * p.field_stride, sqrt(v2));
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            if (s == 6) {
-                k0 = 6 - k0;
-                ++m;
-                s = 1;
-                if (--to_sample == 0) { to_sample = (int)p.out_stride; ++next_k; }
-                if (!__any_sync(0xffffffffu, alive[0] || alive[1]) && (threadIdx.x >= 32 || t + TILE_BUFFERS >= n_tiles)) goto done;
-            } else {
-                ++s;
-            }
-        }
-        if (t + TILE_BUFFERS < n_tiles) {
-            __syncthreads();
-            if (threadIdx.x == 0) issue_tile(t + TILE_BUFFERS);
-        }
-    }
-done:
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-        if (loaded[c]) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) p.state[k * p.n + tid[c]] = y[c][k];
-        }
 }
 
 // ---------------------------------------------------------------- compaction of the live list

@@ -46,7 +46,7 @@ RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
 // (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
-    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r, tan_tol, tan_tol_sure, rad2deg, latc;
+    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc;
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
@@ -74,7 +74,7 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
 #define RB_CONSTS_INIT                                                                              \
     {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
      RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
-     1.0 - RB_EARTH_E2 * RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 100.0 * 1.0000000000003333e-06, 180.0 / RB_PI,           \
+     (1.0 - RB_EARTH_E2 * RB_EARTH_R) / RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 100.0 * 1.0000000000003333e-06, 180.0 / RB_PI,           \
      RB_LAT_FACTOR_COEF / 90.0, RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
      RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
@@ -143,9 +143,10 @@ RB_HD void spacecraft_temperature(double v_norm, double atmo_T, double a_drag_no
 RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, double &B_out) {
     const double p = p2 * inv_p;
     // theta = atan2(z R, p (1 - e2 R)) -> (sin, cos) by normalisation
-    const double ta = z * KC(earth_r), tb = p * KC(one_m_e2r);
-    const double th = rb_rsqrt(fma(ta, ta, tb * tb));
-    const double st = ta * th, ct = tb * th;
+    // (scale invariant: (z R, p (1 - e2 R)) is normalised as (z, p (1 - e2 R) / R) -- one multiply and one constant less)
+    const double tb = p * KC(one_m_e2r_over_r);
+    const double th = rb_rsqrt(fma(z, z, tb * tb));
+    const double st = z * th, ct = tb * th;
     // lat_0 = atan2(z + e2R sin^3 theta, p - e2R cos^3 theta)
     double A = fma(KC(e2r), st * (st * st), z), B = fma(-KC(e2r), ct * (ct * ct), p);
     const double zp = z * inv_p;          // A of every later iterate
@@ -216,7 +217,7 @@ RB_HD double haversine(double lat1, double lon1, double lat2, double lon2) {
 RB_HD double density(double altitude, double abs_latitude_deg, double solar_time, double &T_out) {
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
-    if (altitude < KC(blend_alt)) {
+    if (altitude < RB_SOLAR_BLEND_ALT) {          // 90 km and the layer breakpoints have zero low words: immediates
         const double normalized = rb_rcp(1.0 + rb_exp(-KC(sig_ks) * (altitude - KC(sig_x0))));   // 1 / (1 + e^(-k (x - x0)))
         factor = fma(factor - 1.0, normalized, 1.0);
     }
@@ -224,9 +225,9 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
     // rho = c0 e^arg (latitude_factor factor): every layer funnels into ONE exp, so that a warp whose lanes sit in
     // different layers (isothermal / gradient / top) does not execute one exponential per layer kind
     double arg, c0, T;
-    if (altitude >= KC(top_h)) {  // top layer (i == 7): isothermal + the extra scale-height tail
+    if (altitude >= rb_bp_(7)) {  // top layer (i == 7): isothermal + the extra scale-height tail
         T = KC(top_T);            // P7 / (R_GAS T7) is a constant of the layer
-        arg = (altitude - KC(top_h)) * KC(top_k);
+        arg = (altitude - rb_bp_(7)) * KC(top_k);
         c0 = KC(top_rho0);
     } else {
         // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
@@ -340,108 +341,6 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         }
     }
     a[0] = ax; a[1] = ay; a[2] = az;
-}
-
-// ---- two trajectories per thread -----------------------------------------------------------
-// The B200 FP64 pipe issues one warp-instruction per 2 cycles only when consecutive FP64
-// instructions of the SAME warp are independent; dependent single-chain code saturates at one per
-// 3 cycles however many warps are resident (profiles/r1_variant_sweep.txt, tools/ubench).  The RHS
-// is a long dependent chain, so the step kernel evaluates it for TWO trajectories per thread with
-// the statements of the pair adjacent: every operation below is the scalar acceleration<false>()
-// operation for operation (bit-identical results), written over [2] arrays with unrolled loops so
-// that the pair shares basic blocks; the data-dependent geodetic loop runs until both have
-// converged (finished members are frozen by selects) and the uncommon atmosphere branches fall back
-// to the scalar density().
-#define RB_PAIR _Pragma("unroll") for (int c = 0; c < 2; ++c)
-RB_HD void acceleration2(const double *__restrict__ e, const double r[2][3], const double v[2][3], const Body b[2],
-                         double a[2][3]) {
-    double x[2], y[2], z[2], p2[2], r2[2], ir[2], wx[2], wy[2], wz[2], ax[2], ay[2], az[2], altitude[2];
-    RB_PAIR {
-        x[c] = r[c][0]; y[c] = r[c][1]; z[c] = r[c][2];
-        p2[c] = fma(x[c], x[c], y[c] * y[c]);
-        r2[c] = fma(z[c], z[c], p2[c]);
-        ir[c] = rb_rsqrt(r2[c]);
-    }
-    RB_PAIR {
-        const double ir2 = ir[c] * ir[c], ir3 = ir2 * ir[c];
-        wx[c] = fma(KC(omega), y[c], v[c][0]); wy[c] = fma(-KC(omega), x[c], v[c][1]); wz[c] = v[c][2];
-        const double gk = KC(neg_mu) * ir3;
-        const double f = KC(j2f) * (ir3 * ir2);
-        const double q = (5.0 * ir2) * (z[c] * z[c]);
-        const double fxy = fma(q, f, -f), fz = fma(q, f, -3.0 * f);
-        const double kxy = gk + fxy;
-        ax[c] = fma(kxy, x[c], e[H_NIND + 0]); ay[c] = fma(kxy, y[c], e[H_NIND + 1]); az[c] = fma(gk + fz, z[c], e[H_NIND + 2]);
-        altitude[c] = fma(r2[c], ir[c], -KC(earth_r));
-    }
-    // geodetic pair iteration (geodetic_pair), merged over the two trajectories
-    double ip[2], A[2], B[2], zp[2], ke[2];
-    bool done[2];
-    RB_PAIR {
-        ip[c] = rb_rsqrt(p2[c]);
-        const double p = p2[c] * ip[c];
-        const double ta = z[c] * KC(earth_r), tb = p * KC(one_m_e2r);
-        const double th = rb_rsqrt(fma(ta, ta, tb * tb));
-        const double st = ta * th, ct = tb * th;
-        A[c] = fma(KC(e2r), st * (st * st), z[c]);
-        B[c] = fma(-KC(e2r), ct * (ct * ct), p);
-        zp[c] = z[c] * ip[c];
-        ke[c] = KC(e2r) * ip[c];
-    }
-    RB_PAIR {
-        const double q = rb_rsqrt(fma(B[c], B[c], KC(one_m_e2) * (A[c] * A[c])));
-        const double Bn = fma(-ke[c] * B[c], q, 1.0);
-        done[c] = fabs(fma(A[c], Bn, -(zp[c] * B[c]))) < KC(tan_tol) * fma(B[c], Bn, A[c] * zp[c]);
-        if (!done[c]) { A[c] = zp[c]; B[c] = Bn; }
-    }
-    if (!(done[0] && done[1])) {
-        double zp2[2], g[2], azp[2];
-        RB_PAIR { zp2[c] = zp[c] * zp[c]; g[c] = KC(one_m_e2) * zp2[c]; azp[c] = fabs(zp[c]); }
-        for (int it = 1; it < RB_GEODETIC_MAX_ITER; ++it) {
-            RB_PAIR {
-                const double q2 = rb_rsqrt(fma(B[c], B[c], g[c]));
-                const double Bn2 = fma(-ke[c] * B[c], q2, 1.0);
-                const bool conv = azp[c] * fabs(Bn2 - B[c]) < KC(tan_tol) * fma(B[c], Bn2, zp2[c]);
-                if (!done[c]) {          // a finished member keeps its (stale) iterate, as the scalar break does
-                    if (conv) done[c] = true;
-                    else B[c] = Bn2;
-                }
-            }
-            if (done[0] && done[1]) break;
-        }
-    }
-    // third bodies (fill the latency of the serial latitude -> density -> drag tail)
-    RB_PAIR {
-        {
-            const double dx = e[H_MOON + 0] - x[c], dy = e[H_MOON + 1] - y[c], dz = e[H_MOON + 2] - z[c];
-            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-            const double k3 = KC(moon_k) * (id * id * id);
-            ax[c] = fma(k3, dx, ax[c]); ay[c] = fma(k3, dy, ay[c]); az[c] = fma(k3, dz, az[c]);
-        }
-        {
-            const double dx = e[H_SUN + 0] - x[c], dy = e[H_SUN + 1] - y[c], dz = e[H_SUN + 2] - z[c];
-            const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
-            const double k3 = KC(sun_k) * (id * id * id);
-            ax[c] = fma(k3, dx, ax[c]); ay[c] = fma(k3, dy, ay[c]); az[c] = fma(k3, dz, az[c]);
-        }
-    }
-    double lat_deg[2], rho[2];
-    RB_PAIR lat_deg[c] = pair_abs_latitude_deg(A[c], B[c]);
-    if (altitude[0] >= KC(blend_alt) && altitude[1] >= KC(blend_alt)) {
-        // both in the top layer above the solar-factor blend: the common branch of density(), pairwise
-        RB_PAIR {
-            const double latitude_factor = fma(KC(latc), lat_deg[c], 1.0);
-            rho[c] = (KC(top_rho0) * rb_exp((altitude[c] - KC(top_h)) * KC(top_k))) * (latitude_factor * e[H_SOLAR]);
-        }
-    } else {
-        double T;
-        RB_PAIR rho[c] = density(altitude[c], lat_deg[c], e[H_SOLAR], T);
-    }
-    RB_PAIR {
-        const double w2 = fma(wz[c], wz[c], fma(wx[c], wx[c], wy[c] * wy[c]));
-        const double vn = w2 * rb_rsqrt(w2);
-        const double kd = -(rho[c] * b[c].bc) * vn;
-        a[c][0] = fma(kd, wx[c], ax[c]); a[c][1] = fma(kd, wy[c], ay[c]); a[c][2] = fma(kd, wz[c], az[c]);
-    }
 }
 
 // event function of run_simulation.altitude_event (spacecraft_model.py:496-501)

@@ -274,7 +274,7 @@ class SpacecraftModel:
     # ------------------------------------------------------------------- run_ensemble
     def run_ensemble(self, y0, t0=0.0, dt=1.0, n_steps=0, out_stride=1, Cd=None, A=None, m=None,
                      store_samples=True, steps_per_launch=0, compact=True, early_exit=True, refine=True,
-                     event_altitude=1000.0, table_threads=0, profile=False, skip_negligible_drag=False, overlap=True, pairs=False) -> EnsembleResult:
+                     event_altitude=1000.0, table_threads=0, profile=False, skip_negligible_drag=False, overlap=True) -> EnsembleResult:
         """Propagate N independent initial states y0[N,6] for up to n_steps fixed steps of dt.
 
         Per-trajectory Cd / A / m may be given as arrays [N]; otherwise the model's scalars apply.
@@ -313,7 +313,7 @@ class SpacecraftModel:
                      cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
         flags = (L.RB_FLAG_COMPACT if compact else 0) | (L.RB_FLAG_EARLY_EXIT if early_exit else 0) | \
                 (0 if refine else L.RB_FLAG_NO_REFINE) | (L.RB_FLAG_PROFILE if profile else 0) | \
-                (L.RB_FLAG_SKIP_NEGLIGIBLE_DRAG if skip_negligible_drag else 0) | (0 if overlap else L.RB_FLAG_NO_OVERLAP) | (L.RB_FLAG_PAIRWISE_KERNEL if pairs else 0)
+                (L.RB_FLAG_SKIP_NEGLIGIBLE_DRAG if skip_negligible_drag else 0) | (0 if overlap else L.RB_FLAG_NO_OVERLAP)
         run = L.RbRun(first_step=0, n_steps=int(n_steps), out_stride=int(out_stride),
                       steps_per_launch=int(steps_per_launch), event_altitude=float(event_altitude), flags=flags)
         out = L.RbOut(samples=None if samples is None else samples.data_ptr(),

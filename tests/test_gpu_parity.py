@@ -225,32 +225,6 @@ def test_two_partition_overlap_is_invisible(Model, torch):
     assert torch.equal(c.impact_step, a.impact_step) and torch.equal(c.final_state, a.final_state)
 
 
-def test_pairwise_kernel_is_bit_identical(Model, torch, oracle):
-    """The two-trajectories-per-thread step kernel (used while >= 200k trajectories are live) performs the
-    scalar kernel's arithmetic operation for operation: bit-identical results, odd counts included, and
-    parity against the oracle on a subsample."""
-    from reentry_old_b200.configs import reentry_dispersion_params
-
-    n = 250_001
-    rng = np.random.default_rng(4)
-    m = Model(Cd=1.3, A=14.0, m=5000.0)
-    p = reentry_dispersion_params(n, seed=31)
-    p[: n // 3, 1] = rng.uniform(-85, 85, n // 3)      # spread latitudes: different geodetic iteration counts within pairs
-    p[::7, 5] -= 1.0                                    # steeper entries: partners retire at different times
-    y0 = m.get_initial_states(*p.T)
-    Cd, A, mass = rng.uniform(1, 2.2, n), rng.uniform(5, 30, n), rng.uniform(500, 8000, n)
-    a = m.run_ensemble(y0, dt=0.5, n_steps=2304, out_stride=64, Cd=Cd, A=A, m=mass, pairs=True)
-    b = m.run_ensemble(y0, dt=0.5, n_steps=2304, out_stride=64, Cd=Cd, A=A, m=mass, pairs=False)
-    assert torch.equal(torch.nan_to_num(a.samples, nan=-1.0), torch.nan_to_num(b.samples, nan=-1.0))
-    for k in ("final_state", "impact_step", "status", "n_samples"):
-        assert torch.equal(getattr(a, k), getattr(b, k)), k
-    assert torch.equal(torch.nan_to_num(a.impact_time), torch.nan_to_num(b.impact_time))
-    sub = np.arange(0, n, n // 48)[:48]
-    ref = oracle.propagate(y0[sub].cpu().numpy(), Cd[sub], A[sub], mass[sub], m.epoch, m.gmst0, 0.0, 0.5, 2304, 64)
-    compare_states(samples_np(a)[sub][:, :, :6], ref["samples"][:, :, :6], "pairwise kernel vs oracle")
-    assert np.array_equal(a.impact_step[sub].cpu().numpy(), ref["impact_step"])
-
-
 def test_checkpoint_resume_equals_one_shot(Model, torch):
     """RB_FLAG_RESUME: the output buffers are the checkpoint; chunked propagation == one call, bit for bit."""
     from reentry_old_b200.configs import reentry_dispersion_params
