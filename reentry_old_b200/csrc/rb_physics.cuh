@@ -29,7 +29,7 @@ enum : int {
 // ... and the 96-byte form the step kernel streams through shared memory (rb_ctx_set_time_table converts on the
 // device): only what the hot RHS reads, with the two time-only indirect third-body terms pre-summed and negated
 // so that they ride on the gravity multiply (a = k r - ind, one DFMA per component).
-enum : int { H_SUN = 0, H_MOON = 3, H_NIND = 6, H_SOLAR = 9, H_T = 10, HOT_DOUBLES = 12 };
+enum : int { H_SUN = 0, H_MOON = 3, H_NIND = 6, H_SOLAR = 9, H_T = 10, H_SOLAR_M1 = 11, HOT_DOUBLES = 12 };
 RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
     for (int c = 0; c < 3; ++c) {
         h[H_SUN + c] = e[E_SUN + c];
@@ -38,7 +38,7 @@ RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
     }
     h[H_SOLAR] = e[E_SOLAR];
     h[H_T] = e[E_T];
-    h[11] = 0.0;
+    h[H_SOLAR_M1] = e[E_SOLAR] - 1.0;   // (factor - 1) of the sigmoid blend, :166
 }
 
 // ---- constants of the hot RHS, kept in the constant bank ---------------------------------
@@ -46,14 +46,15 @@ RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
 // (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
-    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc;
+    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc, latc_rad;
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
+    double sig_c, top_c;         // sig_ks sig_x0 ; -top_k top_h  (the exponents as one fma of the altitude)
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
     double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
     double inv_bt[RB_N_LAYERS];  // 1 / T_i
     // the same per-layer constants packed for the hot path: one 64-byte record per layer (three LDC.128 instead of
-    // nine LDC.64 with a lane-dependent index): {h_i, L_i}, {T_i, L_i / T_i}, {k_i, P_i} with k_i = gM/(R* T_i) on
+    // nine LDC.64 with a lane-dependent index): {h_i, L_i}, {T_i, L_i / T_i}, {k_i, P_i / R_GAS} with k_i = gM/(R* T_i) on
     // isothermal layers and gM/(R* L_i) on gradient layers
     double layer[RB_N_LAYERS][8];
 };
@@ -69,15 +70,16 @@ constexpr double rb_powk_(int i) { return rb_gr_(i) == 0.0 ? 0.0 : RB_GM_ / (RB_
 #define RB_L8_(f) {f(0), f(1), f(2), f(3), f(4), f(5), f(6), f(7)}
 constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
 #define RB_LAYER_(i) {rb_bp_(i), rb_gr_(i), rb_bt_(i), rb_gr_(i) / rb_bt_(i),                         \
-                      rb_gr_(i) == 0.0 ? rb_isok_(i) : rb_powk_(i), rb_bpz_(i), 0.0, 0.0}
+                      rb_gr_(i) == 0.0 ? rb_isok_(i) : rb_powk_(i), rb_bpz_(i) / RB_R_GAS, 0.0, 0.0}
 
 #define RB_CONSTS_INIT                                                                              \
     {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
      RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
      (1.0 - RB_EARTH_E2 * RB_EARTH_R) / RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 100.0 * 1.0000000000003333e-06, 180.0 / RB_PI,           \
-     RB_LAT_FACTOR_COEF / 90.0, RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
+     RB_LAT_FACTOR_COEF / 90.0, (RB_LAT_FACTOR_COEF / 90.0) * (180.0 / RB_PI), RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
      RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
+     (RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS) * RB_SIGMOID_X0, -(rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT) * rb_bp_(7),   \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
      RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_)}
 
@@ -174,10 +176,11 @@ RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, doubl
     }
     A_out = A; B_out = B;
 }
-RB_HD double pair_abs_latitude_deg(double A, double B) {
+RB_HD double pair_abs_latitude_rad(double A, double B) {
     const double nr = rb_rsqrt(fma(A, A, B * B));
-    return rb_atan2_unit(fabs(A) * nr, B * nr) * KC(rad2deg);
+    return rb_atan2_unit(fabs(A) * nr, B * nr);
 }
+RB_HD double pair_abs_latitude_deg(double A, double B) { return pair_abs_latitude_rad(A, B) * KC(rad2deg); }
 RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
     double A, B;
     geodetic_pair(p2, inv_p, z, A, B);
@@ -214,20 +217,21 @@ RB_HD double haversine(double lat1, double lon1, double lat2, double lon2) {
 // (spacecraft_model.py:181-188, :71-99, :148-168, :110-127).  solar_time = time-only part of the
 // solar factor from the time table.  The two exponentials of the top layer (:84 and :89) are
 // one exp of the summed exponent.
-RB_HD double density(double altitude, double abs_latitude_deg, double solar_time, double &T_out) {
+RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out) {
+    // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
+    // solar_m1 = solar_time - 1 (both from the time table)
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
     if (altitude < RB_SOLAR_BLEND_ALT) {          // 90 km and the layer breakpoints have zero low words: immediates
-        const double normalized = rb_rcp(1.0 + rb_exp(-KC(sig_ks) * (altitude - KC(sig_x0))));   // 1 / (1 + e^(-k (x - x0)))
-        factor = fma(factor - 1.0, normalized, 1.0);
+        const double normalized = rb_rcp(1.0 + rb_exp(fma(-KC(sig_ks), altitude, KC(sig_c))));   // 1 / (1 + e^(-k (x - x0)))
+        factor = fma(solar_m1, normalized, 1.0);
     }
-    const double latitude_factor = fma(KC(latc), abs_latitude_deg, 1.0);
     // rho = c0 e^arg (latitude_factor factor): every layer funnels into ONE exp, so that a warp whose lanes sit in
     // different layers (isothermal / gradient / top) does not execute one exponential per layer kind
     double arg, c0, T;
     if (altitude >= rb_bp_(7)) {  // top layer (i == 7): isothermal + the extra scale-height tail
         T = KC(top_T);            // P7 / (R_GAS T7) is a constant of the layer
-        arg = (altitude - rb_bp_(7)) * KC(top_k);
+        arg = fma(KC(top_k), altitude, KC(top_c));
         c0 = KC(top_rho0);
     } else {
         // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
@@ -241,7 +245,7 @@ RB_HD double density(double altitude, double abs_latitude_deg, double solar_time
         const double k = lay[4];
         arg = dh * k;                                                   // isothermal: P_i e^(k dh), :84
         if (L != 0.0) arg = k * rb_log1p_small(lay[3] * dh);            // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
-        c0 = lay[5] * rb_rcp(KC(rgas) * T);                             // P / (R_GAS T), :88
+        c0 = lay[5] * rb_rcp(T);                                        // P / (R_GAS T), :88
     }
     T_out = T;
     return (c0 * rb_exp(arg)) * (latitude_factor * factor);
@@ -318,9 +322,13 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         double gA, gB;
         geodetic_pair(p2, ip, z, gA, gB);
         third_bodies();
-        const double lat_deg = pair_abs_latitude_deg(gA, gB);
-        double T;
-        const double rho = density(altitude, lat_deg, e[DIAG ? (int)E_SOLAR : (int)H_SOLAR], T);
+        double T, rho, lat_deg = 0.0;
+        if (DIAG) {
+            lat_deg = pair_abs_latitude_deg(gA, gB);
+            rho = density(altitude, fma(KC(latc), lat_deg, 1.0), e[E_SOLAR], e[E_SOLAR] - 1.0, T);
+        } else {   // radians straight into the latitude factor (the degree conversion folds into the coefficient)
+            rho = density(altitude, fma(KC(latc_rad), pair_abs_latitude_rad(gA, gB), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T);
+        }
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
         const double vn = w2 * rb_rsqrt(w2);
         const double kd = -(rho * b.bc) * vn;

@@ -32,7 +32,9 @@ double hh_geodetic_latitude_deg(double x, double y, double z) {
     const double p2 = x * x + y * y;
     return geodetic_abs_latitude_deg(p2, rb_rsqrt(p2), z);
 }
-double hh_density(double alt, double lat, double solar_time, double *T) { return density(alt, lat, solar_time, *T); }
+double hh_density(double alt, double lat, double solar_time, double *T) {
+    return density(alt, fma(KC(latc), lat, 1.0), solar_time, solar_time - 1.0, *T);
+}
 
 // Same stage arithmetic as k_propagate (Nystrom form, fma chains, table entries), on the host,
 // one trajectory.  table: [(5*n_steps+1)][16].  ys_out: [n_steps+1][6].  Returns the impact step or -1.
