@@ -177,7 +177,7 @@ RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, doubl
     A_out = A; B_out = B;
 }
 RB_HD double pair_abs_latitude_rad(double A, double B) {
-    const double nr = rb_rsqrt(fma(A, A, B * B));
+    const double nr = rb_rsqrt_seed(fma(A, A, B * B));   // approximate length: atan2 is scale free
     return rb_atan2_unit(fabs(A) * nr, B * nr);
 }
 RB_HD double pair_abs_latitude_deg(double A, double B) { return pair_abs_latitude_rad(A, B) * KC(rad2deg); }
