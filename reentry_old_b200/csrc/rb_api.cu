@@ -5,9 +5,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -43,6 +45,7 @@ struct rb_ctx {
     int32_t *d_n_live = nullptr;  // per partition q: [4q] live count, [4q+1] fresh count; [8] edge-sample counter
     int64_t ws_n = 0;
     int32_t *h_poll = nullptr;  // pinned ring
+    int32_t *d_poll = nullptr;  // device address of the same memory
     cudaEvent_t poll_ev[16] = {};
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr, span_ev[2] = {nullptr, nullptr};
     cudaStream_t aux_stream = nullptr;  // second partition
@@ -97,7 +100,8 @@ int32_t rb_ctx_create(rb_ctx **out, int32_t device) {
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_n_live, 12 * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_poll, 16 * sizeof(int32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_poll, 16 * sizeof(int32_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&ctx->d_poll, ctx->h_poll, 0);
     for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->poll_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming);
@@ -288,6 +292,7 @@ struct Part {
     int32_t *n_live = nullptr;       // device [2]: live count, fresh count
     int32_t *block_counts = nullptr; // device, this partition's slice
     int32_t *h_poll = nullptr;       // pinned ring [8]
+    int32_t *d_poll = nullptr;       // its device mapping
     cudaEvent_t *poll_ev = nullptr;  // [8]
 };
 
@@ -336,6 +341,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
         pt.n_live = ctx->d_n_live + 4 * q;
         pt.block_counts = ctx->d_block_counts + ((q == 0) ? 0 : (n / 2 + COMPACT_BLOCK - 1) / COMPACT_BLOCK + 1);
         pt.h_poll = ctx->h_poll + 8 * q;
+        pt.d_poll = ctx->d_poll + 8 * q;
         pt.poll_ev = ctx->poll_ev + 8 * q;
     }
 
@@ -406,21 +412,18 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
                 const unsigned cgrid = (unsigned)((pt.live_bound + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
                 const int32_t *lin = ctx->d_live[pt.cur] + pt.start;
                 k_count_live<<<cgrid, COMPACT_BLOCK, 0, pt.s>>>(lin, pt.n_live, out->status, pt.block_counts);
-                k_scan_blocks<<<1, 1024, 0, pt.s>>>(pt.block_counts, (int)cgrid, pt.n_live + 1);
+                const int slot = (int)(launch_idx & 7);
+                k_scan_blocks<<<1, 1024, 0, pt.s>>>(pt.block_counts, (int)cgrid, pt.n_live + 1, early ? pt.d_poll + slot : nullptr);
                 ctx->stats.kernel_launches += 2;
                 if (compact) {
                     k_scatter_live<<<cgrid, COMPACT_BLOCK, 0, pt.s>>>(lin, pt.n_live, out->status, pt.block_counts,
                                                                      ctx->d_live[pt.cur ^ 1] + pt.start);
-                    CK(cudaMemcpyAsync(pt.n_live, pt.n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, pt.s));
-                    ctx->stats.kernel_launches++;
+                    k_copy_i32<<<1, 1, 0, pt.s>>>(pt.n_live, pt.n_live + 1);
+                    ctx->stats.kernel_launches += 2;
                     pt.cur ^= 1;
                 }
                 CK(cudaGetLastError());
-                if (early) {
-                    const int slot = (int)(launch_idx & 7);
-                    CK(cudaMemcpyAsync(&pt.h_poll[slot], pt.n_live + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, pt.s));
-                    CK(cudaEventRecord(pt.poll_ev[slot], pt.s));
-                }
+                if (early) CK(cudaEventRecord(pt.poll_ev[slot], pt.s));
             }
         }
         ctx->stats.steps_enqueued += steps;
@@ -538,8 +541,13 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         CK(cudaHostAlloc(&ctx->h_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double), cudaHostAllocDefault));
         ctx->h_table_entries = n_entries;
     }
+    const bool trace = getenv("RB_HOST_TRACE") != nullptr;   // phase timings of this call on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(now() - a).count(); };
+    const auto t_begin = now();
     CK(cudaStreamSynchronize(cs));  // previous call may still read the pinned table
     int32_t rc = rb_build_time_table(epoch_jd, gmst0, t0, dt, run->n_steps, ctx->h_table, 0);
+    const double ms_table = ms_since(t_begin);
     if (rc != RB_OK) return rc;
     rc = rb_ctx_set_time_table(ctx, ctx->h_table, run->n_steps, t0, dt, cs);
     if (rc != RB_OK) return rc;
@@ -597,7 +605,11 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     rb_run r2 = *run;
     r2.flags |= RB_FLAG_EARLY_EXIT;
     int64_t steps_done = 0;
+    const auto t_prop = now();
     rc = propagate_impl(ctx, &in, &r2, &out, cs, staged ? &dl : nullptr, &steps_done);
+    const double ms_enqueue = ms_since(t_prop);
+    if (trace) { cudaStreamSynchronize(cs); fprintf(stderr, "rb_propagate_host: table %.2f ms, setup %.2f ms, propagate enqueue %.2f ms, propagate done %.2f ms", ms_table, std::chrono::duration<double, std::milli>(t_prop - t_begin).count() - ms_table, ms_enqueue, ms_since(t_prop)); }
+    const auto t_dl = now();
     if (rc == RB_OK) {
         double *d_aos = (double *)d_state + 6 * n;
         k_soa_to_aos6<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>((const double *)d_state, d_aos, n);
@@ -623,6 +635,7 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "rb_propagate_host download");
     }
+    if (trace) fprintf(stderr, ", download %.2f ms, total %.2f ms\n", ms_since(t_dl), ms_since(t_begin));
     for (int q = 0; q < 2; ++q)
         if (ev[q]) cudaEventDestroy(ev[q]);
     if (n_samples_used) *n_samples_used = !samples ? 0 : (staged ? dl.rows_copied : steps_done / run->out_stride + 1);

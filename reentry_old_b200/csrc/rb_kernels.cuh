@@ -351,8 +351,11 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) k_count_live(const int32_t *liv
     if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
 
-// single block: exclusive scan of block_counts[0..n_blocks) in place; writes the total to n_live_out
-__global__ void __launch_bounds__(1024) k_scan_blocks(int32_t *block_counts, int n_blocks, int32_t *n_live_out) {
+// single block: exclusive scan of block_counts[0..n_blocks) in place; writes the total to n_live_out and, for the
+// host's lagged early-exit poll, into mapped pinned memory (a posted store: a D2H memcpy on the compute stream would
+// queue behind whatever sample traffic occupies the link / the copy engine and stall the next launch)
+__global__ void __launch_bounds__(1024) k_scan_blocks(int32_t *block_counts, int n_blocks, int32_t *n_live_out,
+                                                      int32_t *host_poll) {
     __shared__ int32_t warp_sums[32];
     __shared__ int32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -386,8 +389,13 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(int32_t *block_counts, int
         if (threadIdx.x == 0) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *n_live_out = carry_s;
+    if (threadIdx.x == 0) {
+        *n_live_out = carry_s;
+        if (host_poll) *host_poll = carry_s;
+    }
 }
+
+__global__ void k_copy_i32(int32_t *dst, const int32_t *src) { *dst = *src; }
 
 __global__ void __launch_bounds__(COMPACT_BLOCK) k_scatter_live(const int32_t *live_in, const int32_t *n_live,
                                                                 const uint8_t *status, const int32_t *block_offsets,
