@@ -85,6 +85,9 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
 
 #if defined(__CUDACC__)
 __constant__ Consts c_k = RB_CONSTS_INIT;
+// per-layer records read with a LANE-dependent index: through L1 (LDG.128) instead of the constant bank, whose
+// indexed loads replay once per distinct address in the warp
+__device__ const double __align__(64) g_layer[RB_N_LAYERS][8] = RB_L8_(RB_LAYER_);
 #endif
 static const Consts h_k = RB_CONSTS_INIT;
 #if defined(__CUDA_ARCH__)
@@ -238,7 +241,14 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         int i = (altitude >= KC(bp[4])) ? 4 : 0;
         i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
         i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
+#if defined(__CUDA_ARCH__)
+        const double2 l01 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][0]));
+        const double2 l23 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][2]));
+        const double2 l45 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][4]));
+        const double lay[6] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
+#else
         const double *__restrict__ lay = KC(layer[i]);
+#endif
         const double dh = altitude - lay[0];
         const double L = lay[1];
         T = fma(L, dh, lay[2]);
