@@ -225,22 +225,34 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
     // solar_m1 = solar_time - 1 (both from the time table)
     if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
     double factor = solar_time;
-    if (altitude < RB_SOLAR_BLEND_ALT) {          // 90 km and the layer breakpoints have zero low words: immediates
-        const double normalized = rb_rcp(1.0 + rb_exp(fma(-KC(sig_ks), altitude, KC(sig_c))));   // 1 / (1 + e^(-k (x - x0)))
+    // From here on altitude > 0 (or NaN): the thresholds (90 km, the layer breakpoints) have zero low words, so
+    // `altitude >= b` is the integer compare of the high words -- one issue cycle instead of a DSETP's two.
+    // (CUDA's canonical double NaN has the sign bit set: it compares below every threshold and flows through the
+    // blend and layer 0 as NaN.)
+#if defined(__CUDA_ARCH__)
+    const int ah = __double2hiint(altitude);
+#define RB_ALT_GE(b) (ah >= __double2hiint(b))
+#else
+#define RB_ALT_GE(b) (altitude >= (b))
+#endif
+    if (!RB_ALT_GE(RB_SOLAR_BLEND_ALT)) {
+        // (the exponent lies in [-2.6, 0.8] for 0 < altitude < 90 km: no clamp)
+        const double normalized = rb_rcp(1.0 + rb_exp_bounded(fma(-KC(sig_ks), altitude, KC(sig_c))));   // 1 / (1 + e^(-k (x - x0)))
         factor = fma(solar_m1, normalized, 1.0);
     }
     // rho = c0 e^arg (latitude_factor factor): every layer funnels into ONE exp, so that a warp whose lanes sit in
     // different layers (isothermal / gradient / top) does not execute one exponential per layer kind
     double arg, c0, T;
-    if (altitude >= rb_bp_(7)) {  // top layer (i == 7): isothermal + the extra scale-height tail
+    if (RB_ALT_GE(rb_bp_(7))) {   // top layer (i == 7): isothermal + the extra scale-height tail
         T = KC(top_T);            // P7 / (R_GAS T7) is a constant of the layer
-        arg = fma(KC(top_k), altitude, KC(top_c));
+        arg = rb_exp_clamp(fma(KC(top_k), altitude, KC(top_c)));   // unbounded below as the altitude grows
         c0 = KC(top_rho0);
     } else {
-        // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79)
-        int i = (altitude >= KC(bp[4])) ? 4 : 0;
-        i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
-        i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
+        // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79);
+        // the exponents of these layers lie in [-3.2, 0]
+        int i = RB_ALT_GE(rb_bp_(4)) ? 4 : 0;
+        i += RB_ALT_GE(i == 4 ? rb_bp_(6) : rb_bp_(2)) ? 2 : 0;
+        i += RB_ALT_GE(i == 6 ? 1e300 : (i == 4 ? rb_bp_(5) : (i == 2 ? rb_bp_(3) : rb_bp_(1)))) ? 1 : 0;
 #if defined(__CUDA_ARCH__)
         const double2 l01 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][0]));
         const double2 l23 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][2]));
@@ -258,7 +270,8 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         c0 = lay[5] * rb_rcp(T);                                        // P / (R_GAS T), :88
     }
     T_out = T;
-    return (c0 * rb_exp(arg)) * (latitude_factor * factor);
+    return (c0 * rb_exp_bounded(arg)) * (latitude_factor * factor);
+#undef RB_ALT_GE
 }
 template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
