@@ -27,7 +27,8 @@ def harness():
     os.makedirs(out, exist_ok=True)
     so = os.path.join(out, "host_harness.so")
     src = os.path.join(ROOT, "tests", "host_harness.cu")
-    deps = [src] + [os.path.join(ROOT, "reentry_old_b200", "csrc", f) for f in ("rb_kernels.cuh", "rb_physics.cuh")]
+    csrc = os.path.join(ROOT, "reentry_old_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
         subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
