@@ -46,7 +46,7 @@ RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
 // (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
-    double omega, neg_mu, j2f, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc, latc_rad;
+    double omega, neg_mu, j2f, j2c, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc, latc_rad;
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double sig_c, top_c;         // sig_ks sig_x0 ; -top_k top_h  (the exponents as one fma of the altitude)
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
@@ -74,6 +74,7 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
 
 #define RB_CONSTS_INIT                                                                              \
     {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
+     1.5 * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),                                                 \
      RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
      (1.0 - RB_EARTH_E2 * RB_EARTH_R) / RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 100.0 * 1.0000000000003333e-06, 180.0 / RB_PI,           \
      RB_LAT_FACTOR_COEF / 90.0, (RB_LAT_FACTOR_COEF / 90.0) * (180.0 / RB_PI), RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
@@ -287,17 +288,20 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     // point-mass gravity, :451 : -mu r / |r|^3, and J2, :377-388 : f = 1.5 mu J2 R^2 / r^5 ;
     // a = f r (5 z^2/r^2 - {1,1,3}).  Both are (scalar) * r: the scalars are summed first.
     const double gk = KC(neg_mu) * ir3;
-    const double f = KC(j2f) * (ir3 * ir2);
     const double q = (5.0 * ir2) * (z * z);
-    const double fxy = fma(q, f, -f), fz = fma(q, f, -3.0 * f);
     double ax, ay, az;
-    if (DIAG) {
+    if (DIAG) {   // the two terms separately, as the reference reports them
+        const double f = KC(j2f) * (ir3 * ir2);
+        const double fxy = fma(q, f, -f), fz = fma(q, f, -3.0 * f);
         diag->a_grav[0] = gk * x; diag->a_grav[1] = gk * y; diag->a_grav[2] = gk * z;
         diag->a_j2[0] = fxy * x; diag->a_j2[1] = fxy * y; diag->a_j2[2] = fz * z;
         ax = diag->a_grav[0] + diag->a_j2[0]; ay = diag->a_grav[1] + diag->a_j2[1]; az = diag->a_grav[2] + diag->a_j2[2];
     } else {
-        const double kxy = gk + fxy;
-        ax = fma(kxy, x, e[H_NIND + 0]); ay = fma(kxy, y, e[H_NIND + 1]); az = fma(gk + fz, z, e[H_NIND + 2]);
+        // f = -gk j with j = 1.5 J2 R^2 / r^2:  k_xy = gk (1 + j (1 - q)),  k_z = k_xy + 2 gk j   (q = 5 z^2 / r^2)
+        const double gj = gk * (KC(j2c) * ir2);
+        const double kxy = fma(gj, 1.0 - q, gk);
+        const double kz = fma(gj, 2.0, kxy);
+        ax = fma(kxy, x, e[H_NIND + 0]); ay = fma(kxy, y, e[H_NIND + 1]); az = fma(kz, z, e[H_NIND + 2]);
     }
     // third bodies as a lambda: evaluated inside the drag block (fills the latency of its serial tail)
     // or on their own when the drag block is skipped
