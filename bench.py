@@ -163,10 +163,29 @@ def run_reference_arm(args):
                                        "reference itself is Python+numba and cannot travel to the box)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: point fd 1 at stderr for everything the libraries print (NCCL writes
+    its version banner to stdout) and keep the real stdout for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -349,7 +368,7 @@ def main():
                 "data": "synthetic", "config": config_dict(w, world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_per_pass * K), "roofline": roofline, "cpu_baseline": cpu,
                 "traj_steps_per_pass": total_steps_pass}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
