@@ -119,6 +119,8 @@ def cpu_oracle_rate(w, target_seconds=12.0, n_threads=0):
     from oracle import oracle as O
 
     O.build()
+    if n_threads <= 0:   # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+        n_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     p = w.params
     probe = 64
     y0 = O.get_initial_states(*p[:probe].T, w.gmst0)
