@@ -103,7 +103,8 @@ int64_t rb_time_table_entries(int64_t n_steps); /* 5*n_steps + 1 */
 int32_t rb_build_time_table(double epoch_jd, double gmst0, double t0, double dt, int64_t n_steps,
                             double *host_table, int32_t n_threads);
 
-/* Upload a host table (copied; the context owns the device copy). */
+/* Upload a host table (copied; the context owns the device copy and derives from it, on the device, the 96-byte
+ * entries the step kernel streams: Sun, Moon, -(sum of the two indirect terms), solar factor, t, solar factor - 1). */
 int32_t rb_ctx_set_time_table(rb_ctx *ctx, const double *host_table, int64_t n_steps, double t0,
                               double dt, void *stream);
 
