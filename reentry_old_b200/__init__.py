@@ -8,5 +8,6 @@ not need a GPU, calling it does.
 """
 from ._lib import ReentryB200Error, load as load_library  # noqa: F401
 from .model import DeviceContext, EnsembleResult, Epoch, SpacecraftModel  # noqa: F401
+from .timeutil import epoch_and_gmst  # noqa: F401
 
-__all__ = ["SpacecraftModel", "EnsembleResult", "Epoch", "DeviceContext", "ReentryB200Error", "load_library"]
+__all__ = ["SpacecraftModel", "EnsembleResult", "Epoch", "DeviceContext", "ReentryB200Error", "load_library", "epoch_and_gmst"]
