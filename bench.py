@@ -47,7 +47,7 @@ def _ncu_pipe_numbers():
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "flop_per_traj_step.json")))
         return {k: d[k] for k in ("fp64_pipe_busy_pct_ncu", "fp64_share_of_issued_pct_ncu", "issue_active_pct_ncu",
-                                  "dram_bytes_per_traj_step_ncu") if k in d}
+                                  "issue_port_busy_pct_model", "issue_port_note", "dram_bytes_per_traj_step_ncu") if k in d}
     except Exception:
         return {}
 SAMPLE_BYTES = 64
