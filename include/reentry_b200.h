@@ -231,6 +231,9 @@ typedef struct rb_adaptive_run {
     int64_t max_steps;           /* accepted + rejected attempts per trajectory */
     double event_altitude;       /* 1000.0 */
     double epoch_jd, gmst0;
+    double ephemeris_dt;         /* 0: Sun / Moon / solar factor evaluated at every stage time, as the reference does;
+                                    > 0: evaluated on a grid of this spacing (seconds, on the device) and interpolated
+                                    (4-point Lagrange; error 3e-11 m on the Moon's position at 16 s): faster ensembles */
 } rb_adaptive_run;
 
 typedef struct rb_adaptive_out {

@@ -54,7 +54,7 @@ class RbThermal(C.Structure):
 
 class RbAdaptiveRun(C.Structure):
     _fields_ = [("t0", f64), ("t_bound", f64), ("rtol", f64), ("atol", f64), ("t_eval0", f64), ("t_eval_dt", f64),
-                ("n_eval", i64), ("max_steps", i64), ("event_altitude", f64), ("epoch_jd", f64), ("gmst0", f64)]
+                ("n_eval", i64), ("max_steps", i64), ("event_altitude", f64), ("epoch_jd", f64), ("gmst0", f64), ("ephemeris_dt", f64)]
 
 
 class RbAdaptiveOut(C.Structure):

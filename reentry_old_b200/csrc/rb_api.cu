@@ -36,6 +36,8 @@ struct rb_ctx {
     // time table
     double *d_table = nullptr;      // the step kernel's table (HOT_DOUBLES per entry)
     double *d_table_abi = nullptr;  // the caller's table as uploaded (ENTRY_DOUBLES per entry), converted on the device
+    double *d_eph = nullptr;        // adaptive mode: ephemeris grid nodes (HOT_DOUBLES per node)
+    int64_t eph_capacity = 0;
     int64_t table_capacity = 0;  // entries allocated
     int64_t table_steps = -1;    // steps covered
     double t0 = 0, dt = 0;
@@ -131,6 +133,7 @@ int32_t rb_ctx_destroy(rb_ctx *ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->d_table);
     cudaFree(ctx->d_table_abi);
+    cudaFree(ctx->d_eph);
     cudaFree(ctx->d_live[0]);
     cudaFree(ctx->d_live[1]);
     cudaFree(ctx->d_block_counts);
@@ -672,6 +675,21 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
     p.samples = out->samples; p.sample_stride = out->sample_stride; p.field_stride = out->field_stride;
     p.final_state = out->final_state; p.impact_time = out->impact_time; p.status = out->status;
     p.n_samples = out->n_samples; p.n_accepted = out->n_accepted; p.n_rejected = out->n_rejected;
+    if (run->ephemeris_dt > 0.0) {   // time-only inputs from a grid (built on the device) instead of at every stage time
+        const double span = run->t_bound - run->t0;
+        if (!(span / run->ephemeris_dt < 2.0e8)) return RB_ERR_INVALID_ARG;
+        const int64_t n_nodes = (int64_t)ceil(span / run->ephemeris_dt) + 4;   // one node before t0, two after t_bound
+        if (n_nodes > ctx->eph_capacity) {
+            CK(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(ctx->d_eph);
+            ctx->d_eph = nullptr; ctx->eph_capacity = 0;
+            CK(cudaMalloc(&ctx->d_eph, (size_t)n_nodes * HOT_DOUBLES * sizeof(double)));
+            ctx->eph_capacity = n_nodes;
+        }
+        p.eph = ctx->d_eph; p.eph_t0 = run->t0 - run->ephemeris_dt; p.eph_inv_dt = 1.0 / run->ephemeris_dt; p.eph_n = n_nodes;
+        k_eph_nodes<<<(unsigned)((n_nodes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ctx->d_eph, n_nodes, p.eph_t0, run->ephemeris_dt,
+                                                                                         run->epoch_jd, run->gmst0);
+    }
     k_adaptive<<<(unsigned)((in->n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
     return RB_OK;

@@ -410,11 +410,13 @@ class SpacecraftModel:
 
     # ------------------------------------------------------------ adaptive mode (N4)
     def run_ensemble_adaptive(self, y0, t_span, t_eval_dt, n_eval=None, rtol=1e-8, atol=1e-10, Cd=None, A=None, m=None,
-                              store_samples=True, max_steps=1_000_000, event_altitude=1000.0) -> EnsembleResult:
+                              store_samples=True, max_steps=1_000_000, event_altitude=1000.0, ephemeris_dt=0.0) -> EnsembleResult:
         """The reference's integrator as shipped (solve_ivp RK45, rtol 1e-8, atol 1e-10, spacecraft_model.py:516)
         for N independent initial states, each on its own adaptive time axis.  Samples are the dense-output
         values at t_span[0] + k * t_eval_dt (k < n_eval; default: np.arange(t0, tf, dt), app.py:171) that
-        are not after the terminal altitude event."""
+        are not after the terminal altitude event.  ephemeris_dt > 0 takes Sun / Moon / solar factor from a grid of that
+        spacing (device-built, 4-point Lagrange; 16 s changes positions by < 1e-10 m) instead of evaluating the
+        reference's ephemeris functions at every stage time of every trajectory."""
         torch = _torch()
         ctx = self._ctx()
         if self.sim_type != "RK45":
@@ -443,7 +445,7 @@ class SpacecraftModel:
                      cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
         run = L.RbAdaptiveRun(t0=t0, t_bound=tf, rtol=float(rtol), atol=float(atol), t_eval0=t0, t_eval_dt=float(t_eval_dt),
                               n_eval=int(n_eval), max_steps=int(max_steps), event_altitude=float(event_altitude),
-                              epoch_jd=self.epoch, gmst0=self.gmst0)
+                              epoch_jd=self.epoch, gmst0=self.gmst0, ephemeris_dt=float(ephemeris_dt))
         out = L.RbAdaptiveOut(samples=None if samples is None else samples.data_ptr(), sample_stride=L.RB_SAMPLE_FIELDS * n,
                               field_stride=n, final_state=final_state.data_ptr(), impact_time=impact_time.data_ptr(),
                               status=status.data_ptr(), n_samples=n_samples.data_ptr(), n_accepted=n_acc.data_ptr(),
