@@ -64,6 +64,8 @@ def config_dict(w, n_gpus):
     return {"workload": "C2 Monte Carlo reentry dispersion: 1M perturbed initial states (pos/vel/azimuth), "
                         "dt=0.5 s, until impact, J2+drag+Sun/Moon",
             "n_trajectories_per_gpu": w.n, "n_gpus": n_gpus, "dt": w.dt, "max_steps": w.n_steps,
+            "max_steps_note": "every trajectory impacts within ~1.9 k steps (mean 1362): BASELINE.json's 6000-step cap is "
+                              "never reached; 2048 sizes the time table and the sample buffer",
             "out_stride": w.out_stride, "integrator": "fixed-step Dormand-Prince (scipy RK45 tableau, FSAL)",
             "l2": "working set exceeds L2: ~5.4 GB of sample stores + 48 MB state per step (no flush needed)",
             "sharding": "independent shards, final NCCL gather of summaries" if n_gpus > 1 else "single GPU"}
