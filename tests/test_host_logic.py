@@ -149,6 +149,28 @@ def test_geodetic_iteration_quirk(harness, oracle):
                - 45.0000007295818) < 1e-12
 
 
+def test_geodetic_skipped_confirmation_pass_returns_the_same_iterate(harness, oracle):
+    """geodetic_pair() does not compute the pass that would only confirm convergence when the map's contraction
+    proves its outcome: the returned iterate must still be the reference's, everywhere (consecutive iterates differ
+    by >= 1e-9 deg where it matters, the bar is 1e-13 relative) -- radii from below the surface to 50 R, all
+    latitudes, with the equator and the poles oversampled."""
+    rng = np.random.default_rng(11)
+    n = 20000
+    lat = np.concatenate([rng.uniform(-np.pi / 2, np.pi / 2, n // 2), rng.normal(0, 2e-3, n // 4),
+                          np.sign(rng.normal(size=n // 4)) * (np.pi / 2 - np.abs(rng.normal(0, 2e-3, n // 4)))])
+    rad = 6378137.0 * np.concatenate([rng.uniform(0.95, 1.3, n // 2), 10 ** rng.uniform(0, 1.7, n // 2)])
+    rng.shuffle(rad)
+    lon = rng.uniform(-np.pi, np.pi, n)
+    iters = np.zeros(8, int)
+    for la, lo, r in zip(lat, lon, rad):
+        x, y, z = r * np.cos(la) * np.cos(lo), r * np.cos(la) * np.sin(lo), r * np.sin(la)
+        ref, it = oracle.ecef_to_geodetic(x, y, z, return_iters=True)
+        iters[min(int(it), 7)] += 1
+        got = harness.hh_geodetic_latitude_deg(C.c_double(x), C.c_double(y), C.c_double(z))
+        assert abs(got - abs(ref[0])) <= 1e-13 * max(1.0, abs(ref[0])), (x, y, z, got, ref[0], it)
+    assert iters[2:].sum() > n // 4        # the sample does exercise the multi-pass cases
+
+
 @pytest.mark.parametrize("name,idx", [("c1_single.npz", 0), ("c2_mc.npz", 3), ("edge.npz", 2), ("c3_sso.npz", 1)])
 def test_device_stage_arithmetic_vs_golden(harness, product_lib, golden_dir, name, idx):
     """The kernel's stage arithmetic (fma chains + table entries), run on the host, against the
