@@ -267,7 +267,8 @@ void rb_host_free(void *p);
 
 /* Self-test hook for the library's own FP64 primitives (csrc/rb_math.cuh), elementwise on device
  * arrays: op 0 rcp(x), 1 rsqrt(x), 2 exp(x), 3 log(x) for x in [0.7, 1.3], 4 atan2(x, y) for
- * x, y >= 0 on the unit circle, 5 pow(x, y) for x in [0.7, 1.3].  y may be NULL for unary ops. */
+ * x, y >= 0 on the unit circle, 5 pow(x, y) for x in [0.7, 1.3], 6 log1p(x) for |x| <= 0.3, 7 (1 + x)^y as the
+ * density's pressure law forms it.  y may be NULL for unary ops. */
 int32_t rb_math_probe(rb_ctx *ctx, int32_t op, int64_t n, const double *x, const double *y, double *out,
                       void *stream);
 

@@ -1031,6 +1031,8 @@ __global__ void k_math_probe(int op, int64_t n, const double *x, const double *y
         case 3: r = rb_log_near1(a); break;
         case 4: r = rb_atan2_unit(a, b); break;
         case 5: r = rb_pow_near1(a, b); break;
+        case 6: r = rb_log1p_small(a); break;
+        case 7: r = rb_exp_bounded(b * rb_log1p_small(a)); break;   // the pressure law as density() evaluates it
         default: r = nan("");
     }
     out[i] = r;

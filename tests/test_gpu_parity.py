@@ -450,6 +450,9 @@ def test_math_primitives(torch):
     k = np.array([5.2558, -34.163, -12.201, 12.201, 17.081])[layer]
     x = rng.uniform(lo, hi)
     assert np.max(np.abs(run(5, x, k) / np.power(x, k) - 1.0)) <= 2e-15
+    z = x - 1.0                                                        # T/T_i - 1 = (L/T_i) dh, as density() forms it
+    assert np.max(np.abs(run(6, z) - np.log1p(z))) <= 1.2e-16
+    assert np.max(np.abs(run(7, z, k) / np.power(1.0 + z, k) - 1.0)) <= 1e-14   # k <= 34: exponent error k ulp(log)
     th = np.concatenate([rng.uniform(0, np.pi / 2, n - 5), [0.0, np.pi / 2, np.pi / 4, 1e-9, np.pi / 2 - 1e-9]])
     s, c = np.sin(th), np.cos(th)
     nrm = np.hypot(s, c); s, c = s / nrm, c / nrm
