@@ -172,9 +172,9 @@ RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, doubl
                 B = Bn2;
                 // The iteration map B -> 1 - ke B / sqrt(B^2 + g) contracts by |f'| = ke g / (B^2 + g)^1.5
                 // <= 1.03 e2 R/|r| < 0.008 (|r| > 0.9 R, 0.99 < B < 1), and the right-hand side of the test
-                // shrinks by at most 0.98: d < 122 tol S here PROVES the next pass would break and return
+                // shrinks by at most 0.98: d < 122 tol S (100 is used) here PROVES the next pass would break and return
                 // this Bn2 -- the pass that only confirms convergence is not computed (same returned iterate).
-                if (d < KC(tan_tol_sure) * S) break;
+                if (d < 0x1.a36e3p-14 * S) break;   // 1.0e-4 = 100 tan(1e-6), written with a zero low word (immediate)
             }
         }
     }
