@@ -75,6 +75,9 @@ typedef enum rb_traj_status {
                                    `first_step` (a multiple of out_stride).  in->y0 is ignored; out->final_state,
                                    status, impact_step, impact_time (and samples, indexed by the absolute step) are the
                                    buffers the previous chunk wrote.  Chunked runs equal the one-shot run bit for bit */
+#define RB_FLAG_DIRECT_SAMPLES 128u /* rb_propagate_host, pinned buffer: the step kernel stores EVERY sample row straight
+                                      into host memory (default: dense rows travel by copy engine from a device staging
+                                      buffer, only the sparse rows of the retiring phase are stored directly) */
 #define RB_FLAG_STAGED_SAMPLES 64u /* rb_propagate_host: never write samples directly into pinned host memory */
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */
@@ -253,9 +256,10 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
  * y0 [n][6]; cd/area/mass [n] or NULL; samples [n_out][8][n] or NULL; final_state [n][6].
  * Builds the time table, uploads, propagates, downloads, synchronises.
  * samples: only rows < *n_samples_used are touched.  If the buffer is pinned (rb_host_alloc,
- * cudaHostAlloc, cudaHostRegister) the step kernel stores the samples straight into it (zero-copy)
- * and entries of trajectory i at rows >= n_samples[i] keep what the caller had there; a pageable
- * buffer is filled through a device staging buffer and those entries are NaN. */
+ * cudaHostAlloc, cudaHostRegister) rows travel while they are produced: dense rows by copy engine from a
+ * device staging buffer, the sparse rows of the retiring phase as direct (zero-copy) stores of the step
+ * kernel; entries of trajectory i at rows >= n_samples[i] are NaN or keep what the caller had there.  A
+ * pageable buffer is filled through a device staging buffer after the fact and those entries are NaN. */
 int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double *cd, const double *area,
                           const double *mass, double cd_scalar, double area_scalar, double mass_scalar,
                           double epoch_jd, double gmst0, double t0, double dt, const rb_run *run,

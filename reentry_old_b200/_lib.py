@@ -18,6 +18,8 @@ RB_FLAG_PROFILE = 8
 RB_FLAG_SKIP_NEGLIGIBLE_DRAG = 16
 RB_FLAG_NO_OVERLAP = 32
 RB_FLAG_STAGED_SAMPLES = 64
+RB_FLAG_DIRECT_SAMPLES = 128
+RB_FLAG_DIRECT_SAMPLES = 128
 RB_FLAG_RESUME = 256
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8

@@ -284,6 +284,41 @@ struct LaunchHook {
     virtual ~LaunchHook() {}
 };
 
+// rb_propagate_host with a pinned sample buffer.  Sample rows reach the host two ways:
+//   * while at least RB_DMA_MIN_LIVE_PERCENT of a partition's trajectories are alive, the step kernel writes the rows
+//     into a device staging buffer (NaN-prefilled) and the copy engine moves each finished row slice to the host:
+//     the SMs never touch the link, and the copy engine sustains the full 57 GB/s beside the kernel;
+//   * below that, rows are mostly padding, so the kernel stores the few valid entries straight into the host buffer
+//     (zero-copy).  Those stores are scattered 8-byte PCIe writes that the issuing warps wait on: used for the whole
+//     run they cost 16 ms on C2 (167.6 ms), all of it in the phase where trajectories retire; the copy engine for every
+//     row costs 184 ms (7.7 GB of padded rows).  Switch point swept on C2: 60 % 163.2, 40 % 161.0, 20 % 158.1,
+//     10 % 158.2, 5 % 160.2 ms per pass.
+#ifndef RB_DMA_MIN_LIVE_PERCENT
+#define RB_DMA_MIN_LIVE_PERCENT 20
+#endif
+struct SampleRoute {
+    double *staging = nullptr;   // device, same [row][field][trajectory] layout as the host buffer
+    double *host = nullptr;      // the caller's pinned buffer (host address)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // per partition
+    int64_t rows_via_dma = 0;
+    // back-pressure: done[q][i & 7] completes when the i-th row slice of partition q has reached the host
+    cudaEvent_t done[2][8] = {};
+    int64_t n_dma[2] = {0, 0};
+    int64_t launches_backlogged = 0;
+};
+// The copy engine is used only while the link keeps up: if the slice sent RB_DMA_MAX_BACKLOG launches ago has not
+// arrived, the link (or the host's ingest: 8 ranks of a VM share ~88 GB/s) is the bottleneck, and padded rows would
+// only add bytes to it -- the launch stores its valid samples directly instead.
+#ifndef RB_DMA_MAX_BACKLOG
+#define RB_DMA_MAX_BACKLOG 4
+#endif
+
+__global__ void k_fill_nan_2d(double *p, int64_t width, int64_t height, int64_t pitch) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < width * height) p[(i / width) * pitch + (i % width)] = nan("");
+}
+
 // One partition of the ensemble: its own live list window, counters and stream.  Two partitions on
 // two streams let the ragged tail of one partition's launch (last partial wave, retired lanes)
 // overlap with the body of the other's (+3.6 % on C2, profiles/r1_variant_sweep.txt).
@@ -291,6 +326,7 @@ struct Part {
     int64_t start = 0, count = 0, live_bound = 0;
     int cur = 0;
     bool finished = false;
+    int64_t seen_live = -1;          // live count of the last poll (lagged host view); -1 = nothing retired yet
     cudaStream_t s = nullptr;
     int32_t *n_live = nullptr;       // device [2]: live count, fresh count
     int32_t *block_counts = nullptr; // device, this partition's slice
@@ -305,7 +341,7 @@ __global__ void k_set_counts(int32_t *a, int32_t va, int32_t *b, int32_t vb) {
 }
 
 static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, const rb_out *out, cudaStream_t stream,
-                              LaunchHook *hook, int64_t *steps_done_out) {
+                              LaunchHook *hook, int64_t *steps_done_out, SampleRoute *route = nullptr) {
     if (!ctx || !in || !run || !out) return RB_ERR_INVALID_ARG;
     const int64_t n = in->n;
     if (n < 0 || n > 0x7fffffffLL) return RB_ERR_INVALID_ARG;
@@ -387,6 +423,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
                 CK(cudaEventSynchronize(pt.poll_ev[slot]));
                 const int32_t seen = pt.h_poll[slot];
                 if (compact) pt.live_bound = std::min<int64_t>(pt.live_bound, seen);  // the list only shrinks when compacted
+                pt.seen_live = seen;
                 if (seen == 0) pt.finished = true;
                 seen_total += seen;
             }
@@ -406,9 +443,35 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             sp.live = ctx->d_live[pt.cur] + pt.start;
             sp.n_live = pt.n_live;
             const unsigned grid = (unsigned)((pt.live_bound + RB_BLOCK - 1) / RB_BLOCK);
+            // sample rows this launch writes: k with k * out_stride in (run_step0, run_step0 + steps]
+            const int64_t k_first = sp.run_step0 / run->out_stride + 1, k_last = (sp.run_step0 + steps) / run->out_stride;
+            const bool dense_rows = pt.seen_live < 0 || pt.seen_live * 100 >= pt.count * RB_DMA_MIN_LIVE_PERCENT;
+            bool via_dma = route && out->samples && dense_rows && early && k_last >= k_first;
+            if (via_dma && route->n_dma[q] >= RB_DMA_MAX_BACKLOG &&
+                cudaEventQuery(route->done[q][(route->n_dma[q] - RB_DMA_MAX_BACKLOG) & 7]) == cudaErrorNotReady) {
+                via_dma = false;
+                route->launches_backlogged++;
+            }
+            const size_t slice = (size_t)(k_first * RB_SAMPLE_FIELDS * n + pt.start);   // first element of the partition's slice
+            sp.samples = out->samples;
+            if (via_dma) {   // (NaN first: a trajectory that retired in the last two launches leaves its entries unset)
+                const int64_t hgt = (k_last - k_first + 1) * RB_SAMPLE_FIELDS;
+                k_fill_nan_2d<<<(unsigned)((pt.count * hgt + 255) / 256), 256, 0, pt.s>>>(route->staging + slice, pt.count, hgt, n);
+                sp.samples = route->staging;
+            }
             if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
             else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
             CK(cudaGetLastError());
+            if (via_dma) {
+                CK(cudaEventRecord(route->ev[q], pt.s));
+                CK(cudaStreamWaitEvent(route->copy_stream, route->ev[q], 0));
+                CK(cudaMemcpy2DAsync(route->host + slice, (size_t)n * sizeof(double), route->staging + slice, (size_t)n * sizeof(double),
+                                     (size_t)pt.count * sizeof(double), (size_t)((k_last - k_first + 1) * RB_SAMPLE_FIELDS),
+                                     cudaMemcpyDeviceToHost, route->copy_stream));
+                CK(cudaEventRecord(route->done[q][route->n_dma[q] & 7], route->copy_stream));
+                route->n_dma[q]++;
+                route->rows_via_dma += k_last - k_first + 1;
+            }
             ctx->stats.kernel_launches++;
             ctx->stats.propagate_launches++;
             if ((compact || early) && done + steps < run->n_steps) {
@@ -439,6 +502,10 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
         CK(cudaStreamWaitEvent(stream, ctx->join_ev, 0));
     }
     if (profile) CK(cudaEventRecord(ctx->span_ev[1], stream));
+    if (route && route->rows_via_dma > 0) {   // k_refine may add an event-time sample to a row the copy engine delivered
+        CK(cudaEventRecord(route->ev[0], route->copy_stream));
+        CK(cudaStreamWaitEvent(stream, route->ev[0], 0));
+    }
 
     RefineParams rp{};
     rp.table = ctx->d_table; rp.table_steps = ctx->table_steps; rp.h = ctx->dt; rp.ht = make_htableau(ctx->dt); rp.event_altitude = run->event_altitude;
@@ -608,8 +675,20 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     rb_run r2 = *run;
     r2.flags |= RB_FLAG_EARLY_EXIT;
     int64_t steps_done = 0;
+    SampleRoute route;
+    if (zero_copy && !(run->flags & RB_FLAG_DIRECT_SAMPLES)) {
+        void *d_staging = nullptr;
+        if (host_buf(ctx, 7, (size_t)n_out * row, &d_staging) != RB_OK) { (void)cudaGetLastError(); d_staging = nullptr; }   // no room: direct stores only
+      if (d_staging) {
+        route.staging = (double *)d_staging; route.host = samples; route.copy_stream = ctx->copy_stream;
+        for (int q = 0; q < 2; ++q) { CK(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming)); route.ev[q] = ev[q]; }
+        for (int q = 0; q < 2; ++q)
+            for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&route.done[q][i], cudaEventDisableTiming));
+      }
+    }
     const auto t_prop = now();
-    rc = propagate_impl(ctx, &in, &r2, &out, cs, staged ? &dl : nullptr, &steps_done);
+    rc = propagate_impl(ctx, &in, &r2, &out, cs, staged ? &dl : nullptr, &steps_done, route.staging ? &route : nullptr);
+    if (trace && route.staging) fprintf(stderr, "[dma rows %lld, launches kept off the copy engine by back-pressure %lld] ", (long long)route.rows_via_dma, (long long)route.launches_backlogged);
     const double ms_enqueue = ms_since(t_prop);
     if (trace) { cudaStreamSynchronize(cs); fprintf(stderr, "rb_propagate_host: table %.2f ms, setup %.2f ms, propagate enqueue %.2f ms, propagate done %.2f ms", ms_table, std::chrono::duration<double, std::milli>(t_prop - t_begin).count() - ms_table, ms_enqueue, ms_since(t_prop)); }
     const auto t_dl = now();
@@ -641,6 +720,9 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     if (trace) fprintf(stderr, ", download %.2f ms, total %.2f ms\n", ms_since(t_dl), ms_since(t_begin));
     for (int q = 0; q < 2; ++q)
         if (ev[q]) cudaEventDestroy(ev[q]);
+    for (int q = 0; q < 2; ++q)
+        for (int i = 0; i < 8; ++i)
+            if (route.done[q][i]) cudaEventDestroy(route.done[q][i]);
     if (n_samples_used) *n_samples_used = !samples ? 0 : (staged ? dl.rows_copied : steps_done / run->out_stride + 1);
     return rc;
 }

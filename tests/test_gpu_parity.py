@@ -329,8 +329,8 @@ def test_propagate_host_matches_device_path(Model, torch):
 
 
 def test_propagate_host_zero_copy_samples(Model, torch):
-    """Pinned sample buffers are written directly by the kernel (no staging copy): valid entries equal the
-    device path bit for bit, entries after each trajectory's event keep the caller's fill value."""
+    """Pinned sample buffers: valid entries equal the device path bit for bit whichever way the rows travel;
+    entries after each trajectory's event are NaN or keep the caller's fill value."""
     import ctypes as C
 
     from reentry_old_b200 import _lib as L
@@ -347,7 +347,9 @@ def test_propagate_host_zero_copy_samples(Model, torch):
     fs = torch.empty((n, 6), dtype=torch.float64).pin_memory(); ist = torch.empty(n, dtype=torch.int32).pin_memory()
     it = torch.empty(n, dtype=torch.float64).pin_memory(); st = torch.empty(n, dtype=torch.uint8).pin_memory()
     ns = torch.empty(n, dtype=torch.int32).pin_memory(); used = C.c_int64(0)
-    for flags in (L.RB_FLAG_COMPACT, L.RB_FLAG_COMPACT | L.RB_FLAG_STAGED_SAMPLES):
+    # pinned buffer, default: copy-engine rows while the partition is dense, then direct stores;
+    # RB_FLAG_DIRECT_SAMPLES: direct stores only; RB_FLAG_STAGED_SAMPLES: device staging + NaN fill
+    for flags in (L.RB_FLAG_COMPACT, L.RB_FLAG_COMPACT | L.RB_FLAG_DIRECT_SAMPLES, L.RB_FLAG_COMPACT | L.RB_FLAG_STAGED_SAMPLES):
         samples = torch.full((n_out, 8, n), -7.0, dtype=torch.float64).pin_memory()
         run = L.RbRun(first_step=0, n_steps=n_steps, out_stride=stride, steps_per_launch=32, event_altitude=1000.0, flags=flags)
         rc = ctx.lib.rb_propagate_host(ctx.handle, n, y0h.data_ptr(), None, None, None, 1.3, 14.0, 5000.0, m.epoch, m.gmst0, 0.0,
@@ -358,10 +360,14 @@ def test_propagate_host_zero_copy_samples(Model, torch):
         k = used.value
         ref = r.samples[:k].cpu()
         valid = ~torch.isnan(ref)
-        assert torch.equal(samples[:k][valid], ref[valid])
-        fill = -7.0 if flags == L.RB_FLAG_COMPACT else float("nan")           # zero-copy leaves, staging NaN-fills
+        assert torch.equal(samples[:k][valid], ref[valid]), flags
         rest = samples[:k][~valid]
-        assert bool(torch.isnan(rest).all()) if fill != fill else bool((rest == fill).all())
+        if flags & L.RB_FLAG_STAGED_SAMPLES:
+            assert bool(torch.isnan(rest).all())
+        elif flags & L.RB_FLAG_DIRECT_SAMPLES:
+            assert bool((rest == -7.0).all())                     # untouched: the caller's fill value
+        else:
+            assert bool((torch.isnan(rest) | (rest == -7.0)).all())
         assert bool((samples[k:] == -7.0).all())
         assert torch.equal(ns, r.n_samples.cpu()) and torch.equal(ist, r.impact_step.cpu())
 
