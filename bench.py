@@ -357,8 +357,11 @@ def main():
         d2h = (int(ns_h.to(torch.int64).sum()) * SAMPLE_BYTES if samples_h is not None else 0) + n * (48 + 4 + 8 + 1 + 4)
         e2e = {"value": e2e_total * K / el, "unit": UNIT, "h2d_bytes_per_step": n * 48 + (5 * w.n_steps + 1) * 128,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * el / K,
-               "api": "rb_propagate_host (C ABI, pinned host buffers; time table built on the host inside the call; "
-                      "samples stored by the kernel directly into the pinned host buffer over PCIe)"}
+               "api": "rb_propagate_host (C ABI, pinned host buffers; time table built on the host inside the call; sample "
+                      "rows reach the pinned host buffer while later launches run: dense rows by copy engine from a device "
+                      "staging buffer, the sparse rows of the retiring phase as direct stores of the step kernel)",
+               "d2h_note": "d2h_bytes_per_step counts the valid samples and the summaries the caller receives; rows sent "
+                           "by copy engine also carry NaN padding for trajectories that have already retired"}
         del samples_h
 
     cpu = None
