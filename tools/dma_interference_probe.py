@@ -1,30 +1,32 @@
-"""Does a concurrent copy-engine D2H stream slow the step kernel down?  (GPU box)"""
-import os, sys, time
+"""D2H copy-engine bandwidth alone / beside a register-resident DFMA kernel / beside the step kernel (GPU box)."""
+import os, sys, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from reentry_old_b200 import SpacecraftModel
 from reentry_old_b200.configs import reentry_dispersion_params
+from reentry_old_b200.model import DeviceContext
 
 m = SpacecraftModel(Cd=1.3, A=14.0, m=5000.0)
 y0 = m.get_initial_states(*reentry_dispersion_params(1_000_000, 1234).T)
-src = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")      # 512 MB
+ctx = DeviceContext.get()
+src = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
 dst = torch.empty_like(src, device="cpu").pin_memory()
 side = torch.cuda.Stream()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-def run(with_copy):
-    torch.cuda.synchronize()
-    n_copies = 0
-    t = time.perf_counter()
-    if with_copy:
-        with torch.cuda.stream(side):
-            for _ in range(10):                      # 5 GB queued on the copy engine (~90 ms at 56 GB/s)
-                dst.copy_(src, non_blocking=True); n_copies += 1
-    r = m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=2048, store_samples=False, profile=True)
-    torch.cuda.synchronize()
-    el = time.perf_counter() - t
-    return r.stats["propagate_ms"], el * 1e3, n_copies
+def copies(n=10):
+    with torch.cuda.stream(side):
+        e0.record(side)
+        for _ in range(n):
+            dst.copy_(src, non_blocking=True)
+        e1.record(side)
 
-for _ in range(2): run(False)
-for wc in (False, True, False, True):
-    k, wall, nc = run(wc)
-    print(f"concurrent D2H copies {nc:2d} x 512 MB: k_propagate span {k:.1f} ms, wall {wall:.1f} ms")
+def report(tag):
+    torch.cuda.synchronize()
+    print(f"{tag:42s} D2H 5 GB in {e0.elapsed_time(e1):6.1f} ms = {5.37e3 / e0.elapsed_time(e1):5.1f} GB/s")
+
+copies(); report("warm-up")
+copies(); report("copy engine alone")
+copies(); ctx.fp64_peak_tflops(150.0); report("beside the DFMA peak kernel (150 ms)")
+copies(); m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=2048, store_samples=False); report("beside k_propagate (no samples)")
+copies(); m.run_ensemble(y0, dt=0.5, n_steps=2048, out_stride=2048, store_samples=False, overlap=False); report("beside k_propagate, one partition")
