@@ -389,8 +389,16 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     ip.state = out->final_state; ip.n = n; ip.live = ctx->d_live[0];
     ip.impact_step = out->impact_step; ip.impact_time = out->impact_time; ip.status = out->status;
     ip.samples = out->samples; ip.sample_stride = out->sample_stride; ip.field_stride = out->field_stride;
+    if (route && out->samples && !resume) ip.samples = route->staging;   // row 0 travels by copy engine too
     if (resume) k_init_resume<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ctx->d_live[0], n);
     else k_init<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ip);
+    if (route && out->samples && !resume) {
+        CK(cudaEventRecord(route->ev[0], stream));
+        CK(cudaStreamWaitEvent(route->copy_stream, route->ev[0], 0));
+        CK(cudaMemcpyAsync(route->host, route->staging, (size_t)RB_SAMPLE_FIELDS * n * sizeof(double), cudaMemcpyDeviceToHost,
+                           route->copy_stream));
+        route->rows_via_dma += 1;
+    }
     k_set_counts<<<1, 1, 0, stream>>>(parts[0].n_live, (int32_t)parts[0].count, n_parts > 1 ? parts[1].n_live : nullptr,
                                      n_parts > 1 ? (int32_t)parts[1].count : 0);
     CK(cudaMemsetAsync(ctx->d_n_live + 8, 0, sizeof(int32_t), stream));  // edge-sample counter of k_refine
@@ -616,11 +624,7 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     auto ms_since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(now() - a).count(); };
     const auto t_begin = now();
     CK(cudaStreamSynchronize(cs));  // previous call may still read the pinned table
-    int32_t rc = rb_build_time_table(epoch_jd, gmst0, t0, dt, run->n_steps, ctx->h_table, 0);
-    const double ms_table = ms_since(t_begin);
-    if (rc != RB_OK) return rc;
-    rc = rb_ctx_set_time_table(ctx, ctx->h_table, run->n_steps, t0, dt, cs);
-    if (rc != RB_OK) return rc;
+    int32_t rc = RB_OK;
 
     void *d_y0, *d_state, *d_cam = nullptr, *d_istep, *d_itime, *d_status, *d_ns, *d_samples = nullptr;
     if ((rc = host_buf(ctx, 0, (size_t)n * 6 * 8, &d_y0))) return rc;
@@ -654,6 +658,13 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     if (cd) { d_cd = (double *)d_cam; CK(cudaMemcpyAsync(d_cd, cd, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
     if (area) { d_area = (double *)d_cam + n; CK(cudaMemcpyAsync(d_area, area, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
     if (mass) { d_mass = (double *)d_cam + 2 * n; CK(cudaMemcpyAsync(d_mass, mass, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+    // the time table is built on the host while the initial states are on their way to the device
+    const auto t_table = now();
+    rc = rb_build_time_table(epoch_jd, gmst0, t0, dt, run->n_steps, ctx->h_table, 0);
+    const double ms_table = ms_since(t_table);
+    if (rc != RB_OK) return rc;
+    rc = rb_ctx_set_time_table(ctx, ctx->h_table, run->n_steps, t0, dt, cs);
+    if (rc != RB_OK) return rc;
 
     rb_in in{};
     in.n = n; in.y0 = (const double *)d_y0; in.y0_traj_stride = 6; in.y0_comp_stride = 1;
