@@ -253,6 +253,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     int k0 = 0;                     // slot currently holding Ka_0 (toggles 0 <-> 6, FSAL without a copy)
     int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));  // steps until the next stored sample
     int64_t next_k = p.run_step0 / p.out_stride + 1;
+    double ys[6];   // stage state; equals y_n for the launch's very first evaluation (s == 0)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ys[c] = y[c];
     for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
         const double *tile = tiles + (t % TILE_BUFFERS) * TILE_DOUBLES;
@@ -264,12 +267,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         const double *ent = tile + s * HOT_DOUBLES;   // entry 5 m + min(s, 5) of the tile, advanced with the stage
         while (m < ts) {
             if (alive) {
-                double ys[6];
                 switch (s) {
-                    case 0:
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) ys[c] = y[c];
-                        break;
+                    case 0: break;   // ys = y_n: set before the loop
                     case 1: stage_state<1, BLOCK>(Kt, k0, y, p.ht, ys); break;
                     case 2: stage_state<2, BLOCK>(Kt, k0, y, p.ht, ys); break;
                     case 3: stage_state<3, BLOCK>(Kt, k0, y, p.ht, ys); break;
