@@ -57,6 +57,7 @@ struct Consts {
     // nine LDC.64 with a lane-dependent index): {h_i, L_i}, {T_i, L_i / T_i}, {k_i, P_i / R_GAS} with k_i = gM/(R* T_i) on
     // isothermal layers and gM/(R* L_i) on gradient layers
     double layer[RB_N_LAYERS][8];
+    int32_t bp_hi[RB_N_LAYERS];  // high 32 bits of the altitude breakpoints: `altitude >= h_i` as one integer compare
 };
 
 #define RB_GM_ (-RB_EARTH_GRAVITY * RB_AIR_MOLAR_MASS)
@@ -69,6 +70,16 @@ constexpr double rb_isok_(int i) { return RB_GM_ / (RB_GAS_CONSTANT * rb_bt_(i))
 constexpr double rb_powk_(int i) { return rb_gr_(i) == 0.0 ? 0.0 : RB_GM_ / (RB_GAS_CONSTANT * rb_gr_(i)); }
 #define RB_L8_(f) {f(0), f(1), f(2), f(3), f(4), f(5), f(6), f(7)}
 constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
+constexpr int32_t rb_hi_word_(double x) {   // high 32 bits of a positive normal double (compile time)
+    int e = 0;
+    double m = x;
+    while (m >= 2.0) { m *= 0.5; ++e; }
+    while (m < 1.0) { m *= 2.0; --e; }
+    const uint64_t frac = (uint64_t)((m - 1.0) * 4503599627370496.0);
+    return (int32_t)((((uint64_t)(1023 + e) << 52) | frac) >> 32);
+}
+constexpr int32_t rb_bphi_(int i) { return i == 0 ? 0 : rb_hi_word_(rb_bp_(i)); }
+static_assert(rb_hi_word_(90000.0) == 0x40F5F900 && rb_hi_word_(1.0) == 0x3FF00000, "rb_hi_word_");
 #define RB_LAYER_(i) {rb_bp_(i), rb_gr_(i), rb_bt_(i), rb_gr_(i) / rb_bt_(i),                         \
                       rb_gr_(i) == 0.0 ? rb_isok_(i) : rb_powk_(i), rb_bpz_(i) / RB_R_GAS, 0.0, 0.0}
 
@@ -82,7 +93,7 @@ constexpr double rb_invbt_(int i) { return 1.0 / rb_bt_(i); }
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
      (RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS) * RB_SIGMOID_X0, -(rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT) * rb_bp_(7),   \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
-     RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_)}
+     RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_), RB_L8_(rb_bphi_)}
 
 #if defined(__CUDACC__)
 __constant__ Consts c_k = RB_CONSTS_INIT;
@@ -252,8 +263,13 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         // i = searchsorted(ALTITUDE_BREAKPOINTS, altitude, side='right') - 1 in 0..6 (spacecraft_model.py:79);
         // the exponents of these layers lie in [-3.2, 0]
         int i = RB_ALT_GE(rb_bp_(4)) ? 4 : 0;
-        i += RB_ALT_GE(i == 4 ? rb_bp_(6) : rb_bp_(2)) ? 2 : 0;
-        i += RB_ALT_GE(i == 6 ? 1e300 : (i == 4 ? rb_bp_(5) : (i == 2 ? rb_bp_(3) : rb_bp_(1)))) ? 1 : 0;
+#if defined(__CUDA_ARCH__)
+        i += (ah >= KC(bp_hi[i + 2])) ? 2 : 0;      // high words of the breakpoints (their low words are zero)
+        i += (ah >= KC(bp_hi[i + 1])) ? 1 : 0;
+#else
+        i += (altitude >= KC(bp[i + 2])) ? 2 : 0;
+        i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
+#endif
 #if defined(__CUDA_ARCH__)
         const double2 l01 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][0]));
         const double2 l23 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][2]));
