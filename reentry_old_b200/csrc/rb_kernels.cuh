@@ -49,7 +49,7 @@ __constant__ double c_P[7][4] = {RB_DP_P_ROWS};
 //   v_s = v_n + sum_j (h a_sj) Ka_j ;  r_s = r_n + (c_s h) v_n + sum_j (h^2 abar_sj) Ka_j
 // Stages 1..5 accumulate straight onto the state (every fma has a constant-bank operand); the end point sums the
 // increment first and adds it once, as scipy's y_new = y + h (K^T b) does, so the carried state gets one rounding.
-// Ka_j lives in shared memory at Kt[(slot_j*3 + c)*BLOCK]; slot_0 = k0 (FSAL toggle), slot_j = j.
+// Ka_j lives in shared memory at (32-bit shared address) Kt + (slot_j*3 + c)*BLOCK*8; slot_0 = k0 (FSAL toggle), slot_j = j.
 // k_refine repeats exactly this arithmetic (stage_update below) when it recomputes the crossing step.
 template <int S>
 RB_HD void stage_update(const HTableau &ht, const double k[6][3], const double y[6], double ys[6]) {
@@ -75,15 +75,22 @@ RB_HD void stage_update(const HTableau &ht, const double k[6][3], const double y
     }
 }
 
+// The K rows are addressed through ONE 32-bit shared-memory address kept in a register (the compiler otherwise
+// rebuilds the generic pointer -- thread id, shared window base -- twice per stage).
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state(const double *Kt, int k0, const double y[6], const HTableau &ht,
-                                            double ys[6]) {
+__device__ __forceinline__ void stage_state(uint32_t kt, int k0, const double y[6], const HTableau &ht, double ys[6]) {
     double k[6][3];
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-        const double *Kj = Kt + ((j == 0 ? k0 : j) * K_ROWS) * BLOCK;
+        const uint32_t kj = kt + (uint32_t)(((j == 0 ? k0 : j) * K_ROWS) * BLOCK * 8);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) k[j][c] = Kj[c * BLOCK];
+        for (int c = 0; c < 3; ++c) k[j][c] = lds_f64(kj + (uint32_t)(c * BLOCK * 8));
     }
     stage_update<S>(ht, k, y, ys);
 }
@@ -249,7 +256,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     double g_old = event_g(y, p.event_altitude);
     __syncthreads();  // barrier init visible to all before anyone waits
 
-    double *Kt = Ks + threadIdx.x;  // Ka of slot s, component c at Kt[(s*3 + c)*BLOCK]
+    uint32_t Kt = smem_u32(Ks) + threadIdx.x * 8;   // shared address of Ka slot 0, component 0 of this thread:
+    asm volatile("" : "+r"(Kt));                    // Ka of slot s, component c at Kt + (s*3 + c)*BLOCK*8; opaque, so
+                                                    // that it stays in a register instead of being rebuilt per use
     int k0 = 0;                     // slot currently holding Ka_0 (toggles 0 <-> 6, FSAL without a copy)
     int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));  // steps until the next stored sample
     int64_t next_k = p.run_step0 / p.out_stride + 1;
@@ -279,8 +288,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                 const int slot_s = (s == 6) ? (6 - k0) : s;   // (s == 0 happens only while k0 == 0)
                 double a[3], alt_new;   // alt_new = |r_s| - R of the evaluated stage state
                 acceleration<false, SKIP>(ent, ys, ys + 3, body, a, nullptr, &alt_new);
-                double *Ksl = Kt + (slot_s * K_ROWS) * BLOCK;
-                Ksl[0 * BLOCK] = a[0]; Ksl[1 * BLOCK] = a[1]; Ksl[2 * BLOCK] = a[2];
+                const uint32_t ksl = Kt + (uint32_t)((slot_s * K_ROWS) * BLOCK * 8);
+                sts_f64(ksl, a[0]); sts_f64(ksl + BLOCK * 8, a[1]); sts_f64(ksl + 2 * BLOCK * 8, a[2]);
                 if (s == 6) {
                     // step complete: ys = y_{n+1}; the event function is the altitude the FSAL evaluation just used
                     const double g_new = alt_new - p.event_altitude;
