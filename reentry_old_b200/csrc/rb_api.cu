@@ -453,7 +453,10 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             const unsigned grid = (unsigned)((pt.live_bound + RB_BLOCK - 1) / RB_BLOCK);
             // sample rows this launch writes: k with k * out_stride in (run_step0, run_step0 + steps]
             const int64_t k_first = sp.run_step0 / run->out_stride + 1, k_last = (sp.run_step0 + steps) / run->out_stride;
-            const bool dense_rows = pt.seen_live < 0 || pt.seen_live * 100 >= pt.count * RB_DMA_MIN_LIVE_PERCENT;
+            // (once back-pressure has been seen the link is the bottleneck of this call: from then on only rows without
+            //  padding -- every trajectory of the partition alive -- are worth sending by copy engine)
+            const int64_t min_pct = (route && route->launches_backlogged > 0) ? 100 : RB_DMA_MIN_LIVE_PERCENT;
+            const bool dense_rows = pt.seen_live < 0 || pt.seen_live * 100 >= pt.count * min_pct;
             bool via_dma = route && out->samples && dense_rows && early && k_last >= k_first;
             if (via_dma && route->n_dma[q] >= RB_DMA_MAX_BACKLOG &&
                 cudaEventQuery(route->done[q][(route->n_dma[q] - RB_DMA_MAX_BACKLOG) & 7]) == cudaErrorNotReady) {
