@@ -1,0 +1,62 @@
+"""Static properties of the built sm_100a step kernel (no GPU needed: cuobjdump reads the in-tree library).
+Guards the design points DESIGN.md 5.1 relies on: TMA bulk copies + mbarrier for the time-table tiles, register
+budget for 6 resident blocks per SM, FP64 seeds from MUFU, shared-memory K rows through immediate-offset LDS, and
+the instruction budget of the hot loop."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from reentry_old_b200 import build as B
+
+KERNEL = "_ZN2rb11k_propagateILi128ELi6ELb0EEEvNS_10StepParamsE"
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    lib = B.build()
+    txt = subprocess.run(["cuobjdump", "-sass", "-res-usage", lib], capture_output=True, text=True, check=True).stdout
+    m = re.search(r"Function : " + KERNEL + r"\b(.*?)(?=\n\s*(?:Fatbin|Function : )|\Z)", txt, re.S)
+    assert m, "step kernel not found in the library"
+    return txt, m.group(1)
+
+
+def _ops(body):
+    ops = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", body)
+    return {o: ops.count(o) for o in set(ops)}
+
+
+def test_built_for_sm_100a_only(sass):
+    txt, _ = sass
+    archs = set(re.findall(r"arch = (sm_\w+)", txt))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_step_kernel_uses_tma_bulk_copy_and_mbarrier(sass):
+    _, body = sass
+    assert "UBLKCP" in body                      # cp.async.bulk.shared::cluster.global (TMA bulk copy of a table tile)
+    assert "SYNCS" in body                       # mbarrier arrive / try_wait
+    assert "MUFU.RSQ64H" in body and "MUFU.RCP64H" in body   # FP64 seeds; no libdevice slow paths in the RHS
+
+
+def test_step_kernel_register_and_instruction_budget(sass):
+    txt, body = sass
+    res = re.search(r"Function " + KERNEL + r":\s*\n\s*(.*)", txt)
+    regs = int(re.search(r"REG:(\d+)", res.group(1)).group(1)) if res else None
+    assert regs is not None and regs <= 80, regs          # 6 blocks x 128 threads x 80 registers fit the register file
+    ops = _ops(body)
+    fp64 = sum(ops.get(k, 0) for k in ("DFMA", "DMUL", "DADD", "DSETP"))
+    total = sum(ops.values())
+    assert fp64 <= 420 and total <= 1450, (fp64, total)  # 406 / 1400 at the end of round 1 (7 x that in the first kernel)
+    assert ops.get("LDL", 0) <= 1 and ops.get("STL", 0) <= 2   # one 8-byte value lives on the stack (reloaded once per RHS)
+
+
+def test_step_kernel_shared_memory_accesses_have_immediate_offsets(sass):
+    _, body = sass
+    lds = re.findall(r"LDS(?:\.\d+)?\s+R\d+, \[(R\d+)(\+0x[0-9a-f]+)?\]", body)
+    assert len(lds) >= 60                                 # 63 K-row loads per step + the table entries
+    with_imm = sum(1 for _, off in lds if off)
+    assert with_imm >= 0.8 * len(lds)                     # one base register, offsets folded into the instruction
