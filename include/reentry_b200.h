@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 1
+#define RB_ABI_VERSION 2
 #define RB_TABLE_ENTRY_DOUBLES 16 /* one time-table entry = 128 B */
 #define RB_STAGES_PER_STEP 5      /* distinct new stage times per DP5 step (c = 1/5, 3/10, 4/5, 8/9, 1) */
 #define RB_SAMPLE_FIELDS 8        /* x, y, z, vx, vy, vz, altitude, speed */
@@ -46,7 +46,8 @@ typedef enum rb_error {
     RB_ERR_NO_TIME_TABLE = -3,
     RB_ERR_TABLE_RANGE = -4, /* run asks for steps the staged time table does not cover */
     RB_ERR_NOMEM = -5,
-    RB_ERR_NO_DEVICE = -6
+    RB_ERR_NO_DEVICE = -6,
+    RB_ERR_SAMPLE_CAPACITY = -7 /* packed sample arena or slab list too small for the run */
 } rb_error;
 
 /* status[i] values */
@@ -79,6 +80,11 @@ typedef enum rb_traj_status {
                                       into host memory (default: dense rows travel by copy engine from a device staging
                                       buffer, only the sparse rows of the retiring phase are stored directly) */
 #define RB_FLAG_STAGED_SAMPLES 64u /* rb_propagate_host: never write samples directly into pinned host memory */
+#define RB_FLAG_PACKED_SAMPLES 512u /* samples are written as PACKED SLABS (see rb_sample_slab) instead of dense
+                                      [n_out][8][n] rows: each launch's rows are only as wide as the live ensemble at
+                                      that time, so a run "until impact" writes (and, on the host path, sends over
+                                      PCIe) the valid samples and nothing else.  Needs RB_FLAG_COMPACT | RB_FLAG_EARLY_EXIT
+                                      to narrow the rows; not combinable with RB_FLAG_RESUME */
 #define RB_FLAG_PROFILE 8u      /* bracket every step-kernel launch with CUDA events; rb_propagate then
                                    synchronises the stream at the end and rb_stats.propagate_ms is valid */
 
@@ -149,6 +155,25 @@ typedef struct rb_run {
     uint32_t reserved;
 } rb_run;
 
+/* One packed slab = the sample rows ONE launch of the step kernel wrote for ONE partition of the ensemble
+ * (trajectories [first_traj, first_traj + n_traj)): rows first_row .. first_row + n_rows - 1, each row
+ * [RB_SAMPLE_FIELDS][width] doubles at arena[offset + (k - first_row)*8*width + f*width + j].  Column j is the
+ * j-th trajectory, in ascending index order, of the partition that was still alive when the launch started, i.e.
+ * whose impact_step is -1 or > first_step (order-preserving compaction keeps the live list sorted) -- the column
+ * map is a function of the per-trajectory summaries, no index array travels.  (n_live == n_traj: column j is
+ * trajectory first_traj + j; that is also the case of a run without RB_FLAG_COMPACT, whose list never shrinks.)
+ * Columns >= n_live are padding (the host's view of the live count lags the device by one launch); entries of a
+ * trajectory at rows >= n_samples[i] are NaN. */
+typedef struct rb_sample_slab {
+    int64_t offset;      /* doubles from the start of the arena */
+    int64_t first_row;   /* sample index of the first row (sample k is step k*out_stride) */
+    int64_t n_rows;
+    int64_t first_traj, n_traj;   /* the partition */
+    int64_t width;       /* doubles per field row (>= n_live, multiple of 16) */
+    int64_t first_step;  /* step index (run frame) at which the launch started */
+    int64_t n_live;      /* valid columns; -1 where the call could not know it (rb_propagate: read slab_live) */
+} rb_sample_slab;
+
 typedef struct rb_out {
     /* per-sample output, any layout expressible by two strides (elements), or NULL:
      * field f of sample k of trajectory i at samples[k*sample_stride + f*field_stride + i]. */
@@ -163,6 +188,13 @@ typedef struct rb_out {
     double *impact_time;     /* [n], NaN = none */
     uint8_t *status;         /* [n] rb_traj_status (REQUIRED) */
     int32_t *n_samples;      /* [n] valid samples of trajectory i (grid times not after the event), or NULL */
+    /* RB_FLAG_PACKED_SAMPLES only (ignored otherwise): `samples` is then a device arena of packed_capacity doubles
+     * (sample_stride / field_stride / n_out_capacity unused) */
+    int64_t packed_capacity;
+    rb_sample_slab *slabs;   /* HOST array [slab_capacity], filled while the launches are enqueued */
+    int64_t slab_capacity;   /* two per launch are needed at most (two partitions) */
+    int64_t *n_slabs;        /* HOST out: slabs written */
+    int32_t *slab_live;      /* DEVICE [slab_capacity] or NULL: n_live of every slab, written by its launch */
 } rb_out;
 
 /* Replaces SpacecraftModel.run_simulation (spacecraft_model.py:490-519; solve_ivp call :516)
@@ -266,6 +298,27 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
                           double *samples, int64_t n_out_capacity, double *final_state,
                           int32_t *impact_step, double *impact_time, uint8_t *status, int32_t *n_samples,
                           int64_t *n_samples_used);
+/* The same call with PACKED sample slabs (RB_FLAG_PACKED_SAMPLES is implied): `packed` is a host arena of
+ * packed_capacity doubles (pinned: every slab is sent by ONE contiguous copy-engine transfer as soon as its launch
+ * has finished, while later launches run; no SM ever waits on the link and only live columns cross it), `slabs` a
+ * host array the call fills (n_live included).  The time table is built on the host in chunks while the GPU
+ * already runs, and only as far as the ensemble actually flies.  RB_ERR_SAMPLE_CAPACITY if an arena or slab list
+ * is too small (nothing useful is returned then). */
+int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const double *cd, const double *area,
+                                 const double *mass, double cd_scalar, double area_scalar, double mass_scalar,
+                                 double epoch_jd, double gmst0, double t0, double dt, const rb_run *run,
+                                 double *packed, int64_t packed_capacity, rb_sample_slab *slabs,
+                                 int64_t slab_capacity, int64_t *n_slabs, int64_t *packed_used,
+                                 double *final_state, int32_t *impact_step, double *impact_time, uint8_t *status,
+                                 int32_t *n_samples);
+/* Host-side format conversion (no physics): scatter packed slabs into dense rows dense[k][f][i] (n_out rows;
+ * everything not covered by a valid sample is NaN).  All pointers are HOST memory. */
+int32_t rb_unpack_samples(const double *packed, const rb_sample_slab *slabs, int64_t n_slabs, int64_t n,
+                          const int32_t *impact_step, const uint8_t *status, int64_t n_out, double *dense,
+                          int32_t n_threads);
+/* Generation counter of the context's staged time table (incremented by every rb_ctx_set_time_table and by the
+ * *_host calls, which restage it): a caller that caches "the table for (epoch, gmst0, t0, dt) is staged" compares it. */
+int64_t rb_ctx_table_generation(const rb_ctx *ctx);
 void *rb_host_alloc(int64_t bytes); /* pinned host memory (cudaHostAlloc) or NULL */
 void rb_host_free(void *p);
 

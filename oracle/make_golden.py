@@ -13,6 +13,8 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
   c2_mc.npz            48 Monte-Carlo reentry dispersions (dt = 0.5 s, stride 16), O3 (+O2 on 2)
   c3_sso.npz           8 sun-synchronous 550 km satellites, dt = 10 s, 1 day, stride 360, O3
   c4_geo_heo.npz       4 GEO + 4 HEO, dt = 60 s, 6 days, stride 1440, O3
+  c3_sso_7d.npz        64 sun-synchronous 550 km satellites, dt = 10 s, 7 days, stride 360, O3
+  c4_geo_heo_30d.npz   32 GEO + 32 HEO, dt = 60 s, 30 days, stride 1440, O3
   edge.npz             edge cases: start below the event altitude, steep entry, per-trajectory
                        Cd/A/m, event in the first step, no event within the horizon
   ground_track.npz     N2: per-sample geodetic coordinates, cumulative haversine down-range and
@@ -190,9 +192,8 @@ def c2_mc():
                 o2_1_t_event=o2b["t_event"])
 
 
-def c3_sso(const):
+def c3_sso(const, n=8, days=1.0):
     rng = np.random.default_rng(2345)
-    n = 8
     Cd = np.full(n, 2.2); A = rng.uniform(0.5, 2, n); m = rng.uniform(50, 500, n)
     gmst0 = 1.0
     mdl = R.make_model(2.2, 1.0, 100.0, EPOCH_JD, gmst0)
@@ -200,7 +201,7 @@ def c3_sso(const):
     lat = rng.uniform(-80, 80, n); lon = rng.uniform(-180, 180, n)
     params = np.stack([vcirc + rng.normal(0, 1, n), lat, lon, 550e3 + rng.normal(0, 5e3, n), np.full(n, 352.4), np.zeros(n)], axis=1)
     y0 = np.array([mdl.get_initial_state(*p, gmst=gmst0) for p in params])
-    n_steps, stride, dt = 8640, 360, 10.0
+    n_steps, stride, dt = int(round(8640 * days)), 360, 10.0
     o3 = R.o3_run(y0, Cd, A, m, EPOCH_JD, gmst0, 0.0, dt, n_steps, stride)
     return dict(Cd=Cd, A=A, m=m, epoch_jd=EPOCH_JD, gmst0=gmst0, t0=0.0, dt=dt, n_steps=n_steps, stride=stride,
                 params=params, y0=y0, ys=o3["ys"], impact_step=o3["impact_step"])
@@ -218,18 +219,18 @@ def kepler_to_state(mu, a, e, inc, raan, argp, nu):
     return np.concatenate([Rm @ rp, Rm @ vp])
 
 
-def c4_geo_heo(const):
+def c4_geo_heo(const, half=4, days=6.0):
     rng = np.random.default_rng(3456)
     mu = const.EARTH_MU
     y0 = []
-    for _ in range(4):  # GEO
+    for _ in range(half):  # GEO
         y0.append(kepler_to_state(mu, 42164e3, 0.0, np.radians(abs(rng.normal(0, 0.1))), rng.uniform(0, 2 * np.pi), 0.0, rng.uniform(0, 2 * np.pi)))
     rp, ra = const.EARTH_R + 600e3, const.EARTH_R + 39750e3
-    for _ in range(4):  # Molniya-like HEO
+    for _ in range(half):  # Molniya-like HEO
         y0.append(kepler_to_state(mu, (rp + ra) / 2, (ra - rp) / (ra + rp), np.radians(63.4), rng.uniform(0, 2 * np.pi), np.radians(270.0), rng.uniform(0, 2 * np.pi)))
     y0 = np.array(y0)
     Cd, A, m = 2.2, 10.0, 2000.0
-    n_steps, stride, dt = 8640, 1440, 60.0
+    n_steps, stride, dt = int(round(1440 * days)), 1440, 60.0
     o3 = R.o3_run(y0, Cd, A, m, EPOCH_JD, 0.3, 0.0, dt, n_steps, stride)
     return dict(Cd=Cd, A=A, m=m, epoch_jd=EPOCH_JD, gmst0=0.3, t0=0.0, dt=dt, n_steps=n_steps, stride=stride,
                 y0=y0, ys=o3["ys"], impact_step=o3["impact_step"])
@@ -373,6 +374,10 @@ def main():
     if "--only-thermal" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
         return
+    if "--only-long" in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "c3_sso_7d.npz"), **c3_sso(const, n=64, days=7.0))
+        np.savez_compressed(os.path.join(GOLD, "c4_geo_heo_30d.npz"), **c4_geo_heo(const, half=32, days=30.0))
+        return
     if "--only-ground-track" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
         return
@@ -390,6 +395,8 @@ def main():
     print("c2 done")
     np.savez_compressed(os.path.join(GOLD, "c3_sso.npz"), **c3_sso(const))
     np.savez_compressed(os.path.join(GOLD, "c4_geo_heo.npz"), **c4_geo_heo(const))
+    np.savez_compressed(os.path.join(GOLD, "c3_sso_7d.npz"), **c3_sso(const, n=64, days=7.0))
+    np.savez_compressed(os.path.join(GOLD, "c4_geo_heo_30d.npz"), **c4_geo_heo(const, half=32, days=30.0))
     print("c3/c4 done")
     np.savez_compressed(os.path.join(GOLD, "edge.npz"), **edge_cases(const))
     np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))

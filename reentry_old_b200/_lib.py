@@ -19,8 +19,9 @@ RB_FLAG_SKIP_NEGLIGIBLE_DRAG = 16
 RB_FLAG_NO_OVERLAP = 32
 RB_FLAG_STAGED_SAMPLES = 64
 RB_FLAG_DIRECT_SAMPLES = 128
-RB_FLAG_DIRECT_SAMPLES = 128
 RB_FLAG_RESUME = 256
+RB_FLAG_PACKED_SAMPLES = 512
+RB_ABI_VERSION = 2
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
 RB_DIAG_FIELDS = 23
@@ -44,9 +45,16 @@ class RbRun(C.Structure):
                 ("event_altitude", f64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class RbSampleSlab(C.Structure):
+    _fields_ = [("offset", i64), ("first_row", i64), ("n_rows", i64), ("first_traj", i64), ("n_traj", i64),
+                ("width", i64), ("first_step", i64), ("n_live", i64)]
+
+
 class RbOut(C.Structure):
     _fields_ = [("samples", vp), ("sample_stride", i64), ("field_stride", i64), ("n_out_capacity", i64),
-                ("final_state", vp), ("impact_step", vp), ("impact_time", vp), ("status", vp), ("n_samples", vp)]
+                ("final_state", vp), ("impact_step", vp), ("impact_time", vp), ("status", vp), ("n_samples", vp),
+                ("packed_capacity", i64), ("slabs", C.POINTER(RbSampleSlab)), ("slab_capacity", i64),
+                ("n_slabs", C.POINTER(i64)), ("slab_live", vp)]
 
 
 class RbThermal(C.Structure):
@@ -86,6 +94,11 @@ SIGNATURES = {
     "rb_equations_of_motion": (i32, [vp, i64, vp, vp, f64, f64, vp, vp, vp, f64, f64, f64, C.POINTER(RbThermal), vp, vp]),
     "rb_propagate_host": (i32, [vp, i64, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, f64, C.POINTER(RbRun),
                                 vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]),
+    "rb_propagate_host_packed": (i32, [vp, i64, vp, vp, vp, vp, f64, f64, f64, f64, f64, f64, f64, C.POINTER(RbRun),
+                                       vp, i64, C.POINTER(RbSampleSlab), i64, C.POINTER(i64), C.POINTER(i64),
+                                       vp, vp, vp, vp, vp]),
+    "rb_unpack_samples": (i32, [vp, C.POINTER(RbSampleSlab), i64, i64, vp, vp, i64, vp, i32]),
+    "rb_ctx_table_generation": (i64, [vp]),
     "rb_host_alloc": (vp, [i64]),
     "rb_host_free": (None, [vp]),
     "rb_propagate_adaptive": (i32, [vp, C.POINTER(RbIn), C.POINTER(RbAdaptiveRun), C.POINTER(RbAdaptiveOut), vp]),
@@ -116,6 +129,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    if lib.rb_abi_version() != RB_ABI_VERSION:
+        raise ReentryB200Error(f"{LIB_PATH} has ABI version {lib.rb_abi_version()}, this binding expects {RB_ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 

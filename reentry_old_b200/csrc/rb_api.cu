@@ -46,6 +46,9 @@ struct rb_ctx {
     int32_t *d_block_counts = nullptr;
     int32_t *d_n_live = nullptr;  // per partition q: [4q] live count, [4q+1] fresh count; [8] edge-sample counter
     int64_t ws_n = 0;
+    int64_t *d_edge_slot = nullptr;   // packed sample slabs: [2 n] place of the row at the end of the crossing step
+    int64_t edge_n = 0;
+    int64_t table_generation = 0;
     int32_t *h_poll = nullptr;  // pinned ring
     int32_t *d_poll = nullptr;  // device address of the same memory
     cudaEvent_t poll_ev[16] = {};
@@ -53,10 +56,11 @@ struct rb_ctx {
     cudaStream_t aux_stream = nullptr;  // second partition
     bool events_ready = false;
     // host-path device buffers (grow-only)
-    void *d_host_bufs[8] = {nullptr};
-    size_t d_host_bytes[8] = {0};
+    void *d_host_bufs[9] = {nullptr};
+    size_t d_host_bytes[9] = {0};
     cudaStream_t copy_stream = nullptr;
     cudaStream_t compute_stream = nullptr;
+    cudaStream_t up_stream = nullptr;   // chunked table upload of the packed host path
     double *h_table = nullptr;  // pinned staging for the table
     int64_t h_table_entries = 0;
     rb_stats stats = {0, 0, 0, -1, 0.0};
@@ -85,6 +89,7 @@ const char *rb_strerror(int32_t code) {
         case RB_ERR_TABLE_RANGE: return "run exceeds the staged time table";
         case RB_ERR_NOMEM: return "out of memory";
         case RB_ERR_NO_DEVICE: return "no CUDA device";
+        case RB_ERR_SAMPLE_CAPACITY: return "packed sample arena or slab list too small";
         default: return "unknown error";
     }
 }
@@ -137,6 +142,7 @@ int32_t rb_ctx_destroy(rb_ctx *ctx) {
     cudaFree(ctx->d_live[0]);
     cudaFree(ctx->d_live[1]);
     cudaFree(ctx->d_block_counts);
+    cudaFree(ctx->d_edge_slot);
     cudaFree(ctx->d_n_live);
     cudaFreeHost(ctx->h_poll);
     cudaFreeHost(ctx->h_table);
@@ -149,9 +155,12 @@ int32_t rb_ctx_destroy(rb_ctx *ctx) {
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
     delete ctx;
     return RB_OK;
 }
+
+int64_t rb_ctx_table_generation(const rb_ctx *ctx) { return ctx ? ctx->table_generation : -1; }
 
 int32_t rb_ctx_stats(const rb_ctx *ctx, rb_stats *out) {
     if (!ctx || !out) return RB_ERR_INVALID_ARG;
@@ -213,6 +222,7 @@ int32_t rb_ctx_set_time_table(rb_ctx *ctx, const double *host_table, int64_t n_s
     ctx->table_steps = n_steps;
     ctx->t0 = t0;
     ctx->dt = dt;
+    ctx->table_generation++;
     return RB_OK;
 }
 
@@ -278,9 +288,14 @@ static int32_t ensure_workspace(rb_ctx *ctx, int64_t n, cudaStream_t stream) {
     return RB_OK;
 }
 
-// Called after the launch that completed `steps_done` steps of the run has been enqueued.
+// Called around the launches of a run (host-buffer paths).
 struct LaunchHook {
-    virtual void after_launch(int64_t steps_done, const cudaStream_t *streams, int n_streams) = 0;
+    // before the launch covering table steps [.., step_end) is enqueued; streams = the partition streams it will use
+    virtual int32_t before_launch(int64_t step_end, const cudaStream_t *streams, int n_streams) { (void)step_end; (void)streams; (void)n_streams; return RB_OK; }
+    // after the launch that completed `steps_done` steps of the run has been enqueued on all partition streams
+    virtual void after_launch(int64_t steps_done, const cudaStream_t *streams, int n_streams) { (void)steps_done; (void)streams; (void)n_streams; }
+    // packed slabs: slab `index` has just been enqueued on `stream` (its kernel is the last thing in the stream)
+    virtual void after_slab(int64_t index, const rb_sample_slab &slab, cudaStream_t stream) { (void)index; (void)slab; (void)stream; }
     virtual ~LaunchHook() {}
 };
 
@@ -346,21 +361,40 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     const int64_t n = in->n;
     if (n < 0 || n > 0x7fffffffLL) return RB_ERR_INVALID_ARG;
     const bool resume = (run->flags & RB_FLAG_RESUME) != 0;
-    if ((!in->y0 && !resume) || !out->final_state || !out->status || !out->impact_step) return RB_ERR_INVALID_ARG;
-    if (resume && (run->first_step % run->out_stride) != 0) return RB_ERR_INVALID_ARG;
+    const bool packed = (run->flags & RB_FLAG_PACKED_SAMPLES) != 0 && out->samples;
     if (run->n_steps < 0 || run->first_step < 0 || run->out_stride < 1 || run->out_stride > 0x7fffffffLL)
         return RB_ERR_INVALID_ARG;
+    if ((!in->y0 && !resume) || !out->final_state || !out->status || !out->impact_step) return RB_ERR_INVALID_ARG;
+    if (resume && (run->first_step % run->out_stride) != 0) return RB_ERR_INVALID_ARG;
+    if (packed && (resume || !out->slabs || !out->n_slabs || out->slab_capacity < 1 || out->packed_capacity < 0)) return RB_ERR_INVALID_ARG;
     if (ctx->table_steps < 0) return RB_ERR_NO_TIME_TABLE;
     if (run->first_step + run->n_steps > ctx->table_steps) return RB_ERR_TABLE_RANGE;
     // sample frame: a resumed run indexes samples by the ABSOLUTE (table-frame) step, so that all chunks fill one buffer
     const int64_t frame0 = (run->flags & RB_FLAG_RESUME) ? run->first_step : 0;
-    if (out->samples && out->n_out_capacity < (frame0 + run->n_steps) / run->out_stride + 1) return RB_ERR_INVALID_ARG;
+    if (out->samples && !packed && out->n_out_capacity < (frame0 + run->n_steps) / run->out_stride + 1) return RB_ERR_INVALID_ARG;
+    if (packed) *out->n_slabs = 0;
     ctx->stats = rb_stats{0, 0, 0, -1, 0.0};
     if (steps_done_out) *steps_done_out = 0;
     if (n == 0) return RB_OK;
     CK(cudaSetDevice(ctx->device));
     int32_t rc = ensure_workspace(ctx, n, stream);
     if (rc != RB_OK) return rc;
+    int64_t packed_used = 0, n_slabs = 0;
+    if (packed) {
+        if (n > ctx->edge_n) {
+            CK(cudaStreamSynchronize(stream));
+            cudaFree(ctx->d_edge_slot);
+            ctx->d_edge_slot = nullptr; ctx->edge_n = 0;
+            CK(cudaMalloc(&ctx->d_edge_slot, (size_t)n * 2 * sizeof(int64_t)));
+            ctx->edge_n = n;
+        }
+        // slab 0: the initial states (sample 0) of the whole ensemble, written by k_init
+        const int64_t W0 = (n + 15) & ~(int64_t)15;
+        if (RB_SAMPLE_FIELDS * W0 > out->packed_capacity) return RB_ERR_SAMPLE_CAPACITY;
+        out->slabs[0] = rb_sample_slab{0, 0, 1, 0, n, W0, -1, n};
+        packed_used = RB_SAMPLE_FIELDS * W0;
+        n_slabs = 1;
+    }
 
     const int64_t spl = run->steps_per_launch > 0 ? run->steps_per_launch : 32;
     const bool compact = (run->flags & RB_FLAG_COMPACT) != 0;
@@ -389,6 +423,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     ip.state = out->final_state; ip.n = n; ip.live = ctx->d_live[0];
     ip.impact_step = out->impact_step; ip.impact_time = out->impact_time; ip.status = out->status;
     ip.samples = out->samples; ip.sample_stride = out->sample_stride; ip.field_stride = out->field_stride;
+    if (packed) { ip.sample_stride = RB_SAMPLE_FIELDS * out->slabs[0].width; ip.field_stride = out->slabs[0].width; }
     if (route && out->samples && !resume) ip.samples = route->staging;   // row 0 travels by copy engine too
     if (resume) k_init_resume<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ctx->d_live[0], n);
     else k_init<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ip);
@@ -404,6 +439,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     CK(cudaMemsetAsync(ctx->d_n_live + 8, 0, sizeof(int32_t), stream));  // edge-sample counter of k_refine
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 2;
+    if (packed && hook) hook->after_slab(0, out->slabs[0], stream);
     if (profile) CK(cudaEventRecord(ctx->span_ev[0], stream));
     if (n_parts > 1) {  // fork
         CK(cudaEventRecord(ctx->fork_ev, stream));
@@ -417,6 +453,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     sp.cd_s = in->cd_scalar; sp.area_s = in->area_scalar; sp.mass_s = in->mass_scalar;
     sp.samples = out->samples; sp.sample_stride = out->sample_stride; sp.field_stride = out->field_stride;
     sp.impact_step = out->impact_step; sp.status = out->status;
+    sp.packed = packed ? 1 : 0; sp.edge_slot = packed ? ctx->d_edge_slot : nullptr;
 
     int64_t done = 0;
     int64_t launch_idx = 0;
@@ -444,10 +481,12 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
         sp.n_launch_steps = (int)steps;
         cudaStream_t active[2];
         int n_active = 0;
-        for (int q = 0; q < n_parts; ++q) {
+        for (int q = 0; q < n_parts; ++q)
+            if (!parts[q].finished) active[n_active++] = parts[q].s;
+        if (hook && (rc = hook->before_launch(run->first_step + done + steps, active, n_active)) != RB_OK) break;
+        for (int q = 0; q < n_parts && rc == RB_OK; ++q) {
             Part &pt = parts[q];
             if (pt.finished) continue;
-            active[n_active++] = pt.s;
             sp.live = ctx->d_live[pt.cur] + pt.start;
             sp.n_live = pt.n_live;
             const unsigned grid = (unsigned)((pt.live_bound + RB_BLOCK - 1) / RB_BLOCK);
@@ -465,6 +504,24 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             }
             const size_t slice = (size_t)(k_first * RB_SAMPLE_FIELDS * n + pt.start);   // first element of the partition's slice
             sp.samples = out->samples;
+            sp.k_first = k_first; sp.k_last = k_last;
+            const bool slab = packed && k_last >= k_first;
+            if (packed) {
+                sp.samples = nullptr;   // a launch without a sample step writes nothing
+                if (slab) {
+                    const int64_t W = (pt.live_bound + 15) & ~(int64_t)15;
+                    const int64_t need = (k_last - k_first + 1) * RB_SAMPLE_FIELDS * W;
+                    if (packed_used + need > out->packed_capacity || n_slabs >= out->slab_capacity) { rc = RB_ERR_SAMPLE_CAPACITY; break; }
+                    out->slabs[n_slabs] = rb_sample_slab{packed_used, k_first, k_last - k_first + 1, pt.start, pt.count, W, sp.run_step0, -1};
+                    // biased so that row k of the run is at samples + k * sample_stride (integer arithmetic: the biased
+                    // address may lie below the arena)
+                    sp.samples = (double *)((uintptr_t)(out->samples + packed_used) - (uintptr_t)(k_first * RB_SAMPLE_FIELDS * W) * sizeof(double));
+                    sp.sample_stride = RB_SAMPLE_FIELDS * W; sp.field_stride = W;
+                    sp.sample_row0 = k_first; sp.slab_offset = packed_used;
+                    sp.slab_live = out->slab_live ? out->slab_live + n_slabs : nullptr;
+                    packed_used += need;
+                }
+            }
             if (via_dma) {   // (NaN first: a trajectory that retired in the last two launches leaves its entries unset)
                 const int64_t hgt = (k_last - k_first + 1) * RB_SAMPLE_FIELDS;
                 k_fill_nan_2d<<<(unsigned)((pt.count * hgt + 255) / 256), 256, 0, pt.s>>>(route->staging + slice, pt.count, hgt, n);
@@ -473,6 +530,10 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
             else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
             CK(cudaGetLastError());
+            if (slab) {
+                if (hook) hook->after_slab(n_slabs, out->slabs[n_slabs], pt.s);
+                ++n_slabs;
+            }
             if (via_dma) {
                 CK(cudaEventRecord(route->ev[q], pt.s));
                 CK(cudaStreamWaitEvent(route->copy_stream, route->ev[q], 0));
@@ -503,16 +564,19 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
                 if (early) CK(cudaEventRecord(pt.poll_ev[slot], pt.s));
             }
         }
+        if (rc != RB_OK) break;
         ctx->stats.steps_enqueued += steps;
         done += steps;
         if (hook) hook->after_launch(done, active, n_active);
         ++launch_idx;
     }
+    if (packed) *out->n_slabs = n_slabs;
     if (n_parts > 1) {  // join
         CK(cudaEventRecord(ctx->join_ev, ctx->aux_stream));
         CK(cudaStreamWaitEvent(stream, ctx->join_ev, 0));
     }
     if (profile) CK(cudaEventRecord(ctx->span_ev[1], stream));
+    if (rc != RB_OK) return rc;   // (streams joined; the outputs are incomplete)
     if (route && route->rows_via_dma > 0) {   // k_refine may add an event-time sample to a row the copy engine delivered
         CK(cudaEventRecord(route->ev[0], route->copy_stream));
         CK(cudaStreamWaitEvent(stream, route->ev[0], 0));
@@ -530,6 +594,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     rp.out_stride = run->out_stride; rp.run_first_step = run->first_step - frame0; rp.run_n_steps = frame0 + run->n_steps;
     rp.refine = (run->flags & RB_FLAG_NO_REFINE) ? 0 : 1;
     rp.edge_count = ctx->d_n_live + 8;
+    rp.edge_slot = packed ? ctx->d_edge_slot : nullptr;
     k_refine<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(rp);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
@@ -605,7 +670,7 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
                           double *final_state, int32_t *impact_step, double *impact_time, uint8_t *status,
                           int32_t *n_samples, int64_t *n_samples_used) {
     if (!ctx || !run || n < 0 || !y0 || !final_state || !impact_step || !impact_time || !status) return RB_ERR_INVALID_ARG;
-    if (run->first_step != 0) return RB_ERR_INVALID_ARG;
+    if (run->first_step != 0 || run->n_steps < 0 || run->out_stride < 1 || !(dt > 0)) return RB_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
@@ -739,6 +804,257 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
             if (route.done[q][i]) cudaEventDestroy(route.done[q][i]);
     if (n_samples_used) *n_samples_used = !samples ? 0 : (staged ? dl.rows_copied : steps_done / run->out_stride + 1);
     return rc;
+}
+
+// ------------------------------------------------------------------ host-buffer path, packed sample slabs
+namespace {
+struct EventSet {   // events of one call, destroyed on every exit path
+    std::vector<cudaEvent_t> evs;
+    cudaError_t make(cudaEvent_t *e) {
+        cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        if (r == cudaSuccess) evs.push_back(*e);
+        return r;
+    }
+    ~EventSet() { for (auto e : evs) cudaEventDestroy(e); }
+};
+
+// The step kernel's table (96-byte entries) built on the HOST in chunks while the GPU already runs, and only as
+// far as launches are actually enqueued: a run "until impact" with a generous step cap pays for the steps it flies.
+struct TableFeeder : LaunchHook {
+    rb_ctx *ctx;
+    double epoch_jd, gmst0, t0, dt;
+    int64_t n_steps, built_steps = -1;   // entries 0 .. 5 built_steps are on their way to the device
+    int64_t chunk_steps = 512;
+    std::vector<double> tn;              // t_n exactly as scipy accumulates it (t_{n+1} = t_n + dt)
+    double *h_hot;                       // pinned staging, [entries][HOT_DOUBLES]
+    cudaStream_t up_stream;
+    cudaEvent_t up_ev;
+    cudaError_t err = cudaSuccess;
+    double ms_build = 0.0;
+    int32_t before_launch(int64_t step_end, const cudaStream_t *streams, int n_streams) override {
+        if (step_end <= built_steps) return RB_OK;
+        const int64_t target = std::min(n_steps, ((step_end + chunk_steps - 1) / chunk_steps) * chunk_steps);
+        const int64_t e0 = built_steps < 0 ? 0 : RB_STAGES_PER_STEP * built_steps + 1, e1 = RB_STAGES_PER_STEP * target + 1;
+        const auto t_a = std::chrono::steady_clock::now();
+        if ((int64_t)tn.size() < target + 1) {
+            double t = tn.empty() ? t0 : tn.back();
+            if (tn.empty()) tn.push_back(t);
+            while ((int64_t)tn.size() < target + 1) { t = t + dt; tn.push_back(t); }
+        }
+        const double C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+        const double *tnp = tn.data();
+        double *hot = h_hot;
+        const double ej = epoch_jd, g0 = gmst0, h = dt;
+#ifdef _OPENMP
+        const int n_threads = std::max(omp_get_max_threads(), std::min(omp_get_num_procs(), 16));
+#pragma omp parallel for schedule(static) num_threads(n_threads) if (e1 - e0 > 512)
+#endif
+        for (int64_t e = e0; e < e1; ++e) {
+            double te;
+            if (e == 0) te = tnp[0];
+            else {
+                const int64_t n = (e - 1) / RB_STAGES_PER_STEP;
+                const int s = (int)((e - 1) % RB_STAGES_PER_STEP) + 1;
+                te = (s == 5) ? tnp[n + 1] : tnp[n] + C[s] * h;
+            }
+            double ent[ENTRY_DOUBLES];
+            time_entry(te, ej, g0, ent);
+            hot_entry(ent, hot + e * HOT_DOUBLES);
+        }
+        ms_build += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+        cudaError_t e = cudaMemcpyAsync(ctx->d_table + e0 * HOT_DOUBLES, h_hot + e0 * HOT_DOUBLES,
+                                        (size_t)(e1 - e0) * HOT_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, up_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(up_ev, up_stream);
+        for (int q = 0; q < n_streams && e == cudaSuccess; ++q) e = cudaStreamWaitEvent(streams[q], up_ev, 0);
+        if (e != cudaSuccess) { err = e; return RB_ERR_CUDA; }
+        built_steps = target;
+        return RB_OK;
+    }
+};
+
+// Every slab leaves for the host as ONE contiguous copy-engine transfer as soon as its launch has finished.
+struct SlabSender : TableFeeder {
+    const double *d_arena = nullptr;
+    double *h_arena = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int64_t bytes_sent = 0;
+    void after_slab(int64_t index, const rb_sample_slab &sl, cudaStream_t stream) override {
+        if (!h_arena || err != cudaSuccess) return;
+        cudaEvent_t e = ev[index & 1];   // (a wait captures the record made just before it: two events are plenty)
+        cudaError_t r = cudaEventRecord(e, stream);
+        if (r == cudaSuccess) r = cudaStreamWaitEvent(copy_stream, e, 0);
+        const size_t bytes = (size_t)(sl.n_rows * RB_SAMPLE_FIELDS * sl.width) * sizeof(double);
+        if (r == cudaSuccess) r = cudaMemcpyAsync(h_arena + sl.offset, d_arena + sl.offset, bytes, cudaMemcpyDeviceToHost, copy_stream);
+        if (r != cudaSuccess) err = r;
+        bytes_sent += (int64_t)bytes;
+    }
+};
+}  // namespace
+
+int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const double *cd, const double *area,
+                                 const double *mass, double cd_scalar, double area_scalar, double mass_scalar,
+                                 double epoch_jd, double gmst0, double t0, double dt, const rb_run *run,
+                                 double *packed, int64_t packed_capacity, rb_sample_slab *slabs, int64_t slab_capacity,
+                                 int64_t *n_slabs, int64_t *packed_used, double *final_state, int32_t *impact_step,
+                                 double *impact_time, uint8_t *status, int32_t *n_samples) {
+    if (!ctx || !run || n < 0 || !y0 || !final_state || !impact_step || !impact_time || !status) return RB_ERR_INVALID_ARG;
+    if (run->first_step != 0 || run->n_steps < 0 || run->out_stride < 1 || !(dt > 0)) return RB_ERR_INVALID_ARG;
+    if (run->flags & RB_FLAG_RESUME) return RB_ERR_INVALID_ARG;
+    if (packed && (!slabs || !n_slabs || slab_capacity < 1 || packed_capacity < 0)) return RB_ERR_INVALID_ARG;
+    if (n_slabs) *n_slabs = 0;
+    if (packed_used) *packed_used = 0;
+    if (n == 0) return RB_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->compute_stream) CK(cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+    if (!ctx->up_stream) CK(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->compute_stream;
+    const bool trace = getenv("RB_HOST_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+    // everything of the previous call on this context has drained (it synchronised), so buffers may be regrown
+    int32_t rc = RB_OK;
+    void *d_y0, *d_state, *d_cam = nullptr, *d_istep, *d_itime, *d_status, *d_ns, *d_arena = nullptr, *d_slab_live = nullptr;
+    if ((rc = host_buf(ctx, 0, (size_t)n * 6 * 8, &d_y0))) return rc;
+    if ((rc = host_buf(ctx, 1, (size_t)n * 6 * 8 * 2, &d_state))) return rc;  // SoA state + AoS transpose
+    if ((rc = host_buf(ctx, 2, (size_t)n * 3 * 8, &d_cam))) return rc;
+    if ((rc = host_buf(ctx, 3, (size_t)n * 4, &d_istep))) return rc;
+    if ((rc = host_buf(ctx, 4, (size_t)n * 8, &d_itime))) return rc;
+    if ((rc = host_buf(ctx, 5, (size_t)n, &d_status))) return rc;
+    if ((rc = host_buf(ctx, 6, (size_t)n * 4, &d_ns))) return rc;
+    if (packed) {
+        if ((rc = host_buf(ctx, 7, (size_t)packed_capacity * 8, &d_arena))) return rc;
+        if ((rc = host_buf(ctx, 8, (size_t)slab_capacity * 4, &d_slab_live))) return rc;
+    }
+    // time table: device capacity for the whole cap, contents fed chunk by chunk (TableFeeder)
+    const int64_t n_entries = rb_time_table_entries(run->n_steps);
+    if (n_entries > ctx->table_capacity) {
+        cudaFree(ctx->d_table); cudaFree(ctx->d_table_abi);
+        ctx->d_table = ctx->d_table_abi = nullptr; ctx->table_capacity = 0;
+        CK(cudaMalloc(&ctx->d_table, (size_t)n_entries * HOT_DOUBLES * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_table_abi, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double)));
+        ctx->table_capacity = n_entries;
+    }
+    if (n_entries > ctx->h_table_entries) {
+        cudaFreeHost(ctx->h_table);
+        ctx->h_table = nullptr; ctx->h_table_entries = 0;
+        CK(cudaHostAlloc(&ctx->h_table, (size_t)n_entries * ENTRY_DOUBLES * sizeof(double), cudaHostAllocDefault));
+        ctx->h_table_entries = n_entries;
+    }
+    ctx->table_steps = run->n_steps; ctx->t0 = t0; ctx->dt = dt;
+    ctx->table_generation++;   // (a caller's cached "my table is staged" no longer holds)
+
+    EventSet events;
+    SlabSender hook;
+    hook.ctx = ctx; hook.epoch_jd = epoch_jd; hook.gmst0 = gmst0; hook.t0 = t0; hook.dt = dt; hook.n_steps = run->n_steps;
+    hook.h_hot = ctx->h_table; hook.up_stream = ctx->up_stream;
+    hook.d_arena = (const double *)d_arena; hook.h_arena = packed; hook.copy_stream = ctx->copy_stream;
+    CK(events.make(&hook.up_ev));
+    CK(events.make(&hook.ev[0]));
+    CK(events.make(&hook.ev[1]));
+
+    CK(cudaMemcpyAsync(d_y0, y0, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, cs));
+    double *d_cd = nullptr, *d_area = nullptr, *d_mass = nullptr;
+    if (cd) { d_cd = (double *)d_cam; CK(cudaMemcpyAsync(d_cd, cd, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+    if (area) { d_area = (double *)d_cam + n; CK(cudaMemcpyAsync(d_area, area, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+    if (mass) { d_mass = (double *)d_cam + 2 * n; CK(cudaMemcpyAsync(d_mass, mass, (size_t)n * 8, cudaMemcpyHostToDevice, cs)); }
+
+    rb_in in{};
+    in.n = n; in.y0 = (const double *)d_y0; in.y0_traj_stride = 6; in.y0_comp_stride = 1;
+    in.cd = d_cd; in.area = d_area; in.mass = d_mass;
+    in.cd_scalar = cd_scalar; in.area_scalar = area_scalar; in.mass_scalar = mass_scalar;
+    rb_out out{};
+    out.samples = (double *)d_arena; out.packed_capacity = packed_capacity;
+    out.slabs = slabs; out.slab_capacity = slab_capacity; out.slab_live = (int32_t *)d_slab_live;
+    int64_t ns_local = 0;
+    out.n_slabs = &ns_local;
+    out.final_state = (double *)d_state; out.impact_step = (int32_t *)d_istep; out.impact_time = (double *)d_itime;
+    out.status = (uint8_t *)d_status; out.n_samples = (int32_t *)d_ns;
+    rb_run r2 = *run;
+    r2.flags |= RB_FLAG_EARLY_EXIT | RB_FLAG_COMPACT | (packed ? RB_FLAG_PACKED_SAMPLES : 0u);
+    r2.flags &= ~(uint32_t)RB_FLAG_PROFILE;
+    int64_t steps_done = 0;
+    const auto t_prop = std::chrono::steady_clock::now();
+    rc = propagate_impl(ctx, &in, &r2, &out, cs, &hook, &steps_done);
+    const double ms_enqueue = ms_since(t_prop);
+    cudaError_t e = hook.err;
+    if (rc == RB_OK && e == cudaSuccess) {
+        double *d_aos = (double *)d_state + 6 * n;
+        k_soa_to_aos6<<<(unsigned)((n + 255) / 256), 256, 0, cs>>>((const double *)d_state, d_aos, n);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(final_state, d_aos, (size_t)n * 6 * 8, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(impact_step, d_istep, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(impact_time, d_itime, (size_t)n * 8, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && n_samples) e = cudaMemcpyAsync(n_samples, d_ns, (size_t)n * 4, cudaMemcpyDeviceToHost, cs);
+    }
+    // drain: the call returns with every buffer final (also on errors: the copy engine may still be writing `packed`)
+    int32_t edge = 0;
+    std::vector<int32_t> live((size_t)std::max<int64_t>(ns_local, 1));
+    if (rc == RB_OK && e == cudaSuccess) {
+        e = cudaMemcpyAsync(&edge, ctx->d_n_live + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && packed && ns_local > 0)
+            e = cudaMemcpyAsync(live.data(), d_slab_live, (size_t)ns_local * 4, cudaMemcpyDeviceToHost, cs);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(cs);
+    if (e == cudaSuccess) e = e2;
+    if (rc == RB_OK && e == cudaSuccess && packed && edge > 0) {
+        // a grid sample coincided with an event time and was added by k_refine after its slab had been sent
+        // (measure-zero case): send the arena again
+        e = cudaMemcpyAsync(packed, d_arena, (size_t)hook.bytes_sent, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    }
+    e2 = cudaStreamSynchronize(ctx->copy_stream);
+    if (e == cudaSuccess) e = e2;
+    e2 = cudaStreamSynchronize(ctx->up_stream);
+    if (e == cudaSuccess) e = e2;
+    e2 = cudaStreamSynchronize(ctx->aux_stream);
+    if (e == cudaSuccess) e = e2;
+    if (rc == RB_OK && e != cudaSuccess) rc = cuda_fail(ctx, e, "rb_propagate_host_packed");
+    if (rc == RB_OK && packed) {
+        for (int64_t i = 1; i < ns_local; ++i) slabs[i].n_live = live[(size_t)i];
+        *n_slabs = ns_local;
+        if (packed_used) *packed_used = ns_local ? slabs[ns_local - 1].offset + slabs[ns_local - 1].n_rows * RB_SAMPLE_FIELDS * slabs[ns_local - 1].width : 0;
+    }
+    if (trace)
+        fprintf(stderr, "rb_propagate_host_packed: table build %.2f ms (%lld of %lld steps), enqueue %.2f ms, total %.2f ms, %lld slabs, %.3f GB sent\n",
+                hook.ms_build, (long long)hook.built_steps, (long long)run->n_steps, ms_enqueue, ms_since(t_begin), (long long)ns_local, hook.bytes_sent * 1e-9);
+    return rc;
+}
+
+int32_t rb_unpack_samples(const double *packed, const rb_sample_slab *slabs, int64_t n_slabs, int64_t n,
+                          const int32_t *impact_step, const uint8_t *status, int64_t n_out, double *dense, int32_t n_threads) {
+    if (!packed || !slabs || n_slabs < 0 || n < 0 || !impact_step || !status || n_out < 0 || !dense) return RB_ERR_INVALID_ARG;
+    const double qnan = nan("");
+    const int64_t total = n_out * RB_SAMPLE_FIELDS * n;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = std::max(omp_get_max_threads(), std::min(omp_get_num_procs(), 16));
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+#endif
+    for (int64_t i = 0; i < total; ++i) dense[i] = qnan;
+    std::vector<int32_t> cols;
+    for (int64_t s = 0; s < n_slabs; ++s) {
+        const rb_sample_slab &sl = slabs[s];
+        if (sl.first_row + sl.n_rows > n_out || sl.first_traj < 0 || sl.first_traj + sl.n_traj > n) return RB_ERR_INVALID_ARG;
+        cols.clear();   // column map: trajectories of the partition still alive when the launch started, ascending
+        const bool identity = sl.n_live == sl.n_traj;   // nothing retired yet, or a run without compaction (the list never shrinks)
+        for (int64_t i = sl.first_traj; i < sl.first_traj + sl.n_traj; ++i)
+            if (identity || status[i] == RB_TRAJ_ALIVE || impact_step[i] > sl.first_step) cols.push_back((int32_t)i);
+        if ((int64_t)cols.size() > sl.width || (sl.n_live >= 0 && (int64_t)cols.size() != sl.n_live)) return RB_ERR_INVALID_ARG;
+        const int64_t nc = (int64_t)cols.size();
+        const int32_t *cp = cols.data();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(n_threads) collapse(2)
+#endif
+        for (int64_t r = 0; r < sl.n_rows; ++r)
+            for (int f = 0; f < RB_SAMPLE_FIELDS; ++f) {
+                const double *src = packed + sl.offset + (r * RB_SAMPLE_FIELDS + f) * sl.width;
+                double *dst = dense + ((sl.first_row + r) * RB_SAMPLE_FIELDS + f) * n;
+                for (int64_t j = 0; j < nc; ++j) dst[cp[j]] = src[j];
+            }
+    }
+    (void)n_threads;
+    return RB_OK;
 }
 
 void *rb_host_alloc(int64_t bytes) {

@@ -39,7 +39,7 @@ constexpr int TILE_BUFFERS = RB_TILE_BUFFERS;  // 1 = single buffer (TMA latency
 constexpr int TILE_STEPS = RB_TILE_STEPS;                                      // steps per time-table tile
 constexpr int TILE_ENTRIES = RB_STAGES_PER_STEP * TILE_STEPS + 1;  // 41 entries
 constexpr int TILE_DOUBLES = TILE_ENTRIES * HOT_DOUBLES;            // 492 doubles = 3936 B
-constexpr int K_SLOTS = 7;                                          // Ka_0..Ka_6 (acceleration rows only)
+constexpr int K_SLOTS = 6;                                          // Ka_0..Ka_5 (acceleration rows only; Ka_6 = next step's Ka_0 goes to slot 0)
 constexpr int K_ROWS = 3;
 
 __constant__ Tableau c_T = make_tableau();  // run-time operands from the constant bank
@@ -83,14 +83,15 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+// Stage state of stage S from the K rows in shared memory: Ka_j, component c at Kt + (j*3 + c)*BLOCK*8 (Kt = 32-bit
+// shared address of this thread's slot-0 entry; all offsets are immediates of the LDS).
 template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state(uint32_t kt, int k0, const double y[6], const HTableau &ht, double ys[6]) {
+__device__ __forceinline__ void stage_state(uint32_t kt, const double y[6], const HTableau &ht, double ys[6]) {
     double k[6][3];
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-        const uint32_t kj = kt + (uint32_t)(((j == 0 ? k0 : j) * K_ROWS) * BLOCK * 8);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) k[j][c] = lds_f64(kj + (uint32_t)(c * BLOCK * 8));
+        for (int c = 0; c < 3; ++c) k[j][c] = lds_f64(kt + (uint32_t)((j * K_ROWS + c) * BLOCK * 8));
     }
     stage_update<S>(ht, k, y, ys);
 }
@@ -118,6 +119,16 @@ struct StepParams {
     int64_t sample_stride, field_stride;
     int32_t *impact_step;
     uint8_t *status;
+    // packed sample slabs (RB_FLAG_PACKED_SAMPLES): `samples` is the base of THIS launch's slab, whose first row is
+    // sample `sample_row0`, MINUS sample_row0 * sample_stride (row k of the run at samples + k * sample_stride, as in
+    // dense mode); the column of a trajectory is its position in the launch's live list (dense mode: its index).
+    // Rows are therefore as wide as the live ensemble, not as the initial one.
+    int packed;
+    int64_t k_first, k_last;   // sample rows this launch writes (k_last < k_first: none); host-computed (no 64-bit division in the kernel)
+    int64_t sample_row0;
+    int64_t slab_offset;       // element offset of the slab within the arena (for edge_slot)
+    int32_t *slab_live;        // device scalar or NULL: live count at launch start (= valid columns of the slab)
+    int64_t *edge_slot;        // [2n] packed mode: arena offset + field stride of the row at the end of the crossing step
 };
 
 // ---------------------------------------------------------------- PTX helpers (TMA bulk + mbarrier)
@@ -197,11 +208,54 @@ __global__ void k_init(const InitParams p) {
     }
 }
 
+// packed slabs: rows first..last (sample indices) of a column that will not be written any more get NaN, so that a
+// slab needs no prefill (a lane retires once; at most steps_per_launch / out_stride rows are left in its launch)
+// (scalars, not the parameter struct: taking its address would make the kernel copy it to local memory)
+__device__ __noinline__ void nan_rows_at(double *column, int64_t sample_stride, int64_t field_stride, int64_t n_rows) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t k = 0; k < n_rows; ++k) {
+        double *sp = column + k * sample_stride;
+#pragma unroll
+        for (int c = 0; c < RB_SAMPLE_FIELDS; ++c) st_stream(sp + c * field_stride, qnan);
+    }
+}
+#define nan_rows(p, col, first, last) \
+    nan_rows_at((p).samples + (first) * (p).sample_stride + (col), (p).sample_stride, (p).field_stride, (last) - (first) + 1)
+
 // ---------------------------------------------------------------- the hot kernel
-// Shared memory: [2 x tile][Ka slots: 7 x 3 x BLOCK doubles][2 mbarriers]
+// Shared memory per block: [2 x tile][Ka slots: 6 x 3 x BLOCK][y_n backup: 6 x BLOCK][bc, g_old: 2 x BLOCK][2 mbarriers]
+constexpr int PARK_ROWS = 8;   // per-thread doubles parked in shared memory: y_n[6], bc, g_old
 template <int BLOCK>
 constexpr size_t propagate_smem_bytes() {
-    return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + K_SLOTS * K_ROWS * BLOCK) + 2 * sizeof(uint64_t);
+    return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + (K_SLOTS * K_ROWS + PARK_ROWS) * BLOCK) + 2 * sizeof(uint64_t);
+}
+
+// The acceleration evaluation exists ONCE in the kernel, as a subroutine the seven evaluation sites of a step call
+// (ptxas allocates registers across the call: no ABI spills).  The earlier form -- one flattened stage loop around an
+// inlined evaluation with a `switch` over the stage-state arithmetic -- spent ~40 of its ~430 instructions per stage
+// on dispatch (jump table, K-slot select, loop state); a call and a return cost 3.
+//   ent   32-bit shared address of the 96-byte time-table entry of the stage time
+//   park  32-bit shared address of this thread's parked values (bc at row 6)
+//   kdst  32-bit shared address where a[0..2] go (this thread's column of the K slot)
+// Returns |r| - R (the event function's altitude) of the evaluated state.
+#ifndef RB_RHS_INLINE
+#define RB_RHS_INLINE 0   // 1: the evaluation is inlined at its seven sites (no call / argument moves; ~45 KB of code)
+#endif
+#if RB_RHS_INLINE
+#define RB_RHS_LINKAGE __forceinline__
+#else
+#define RB_RHS_LINKAGE __noinline__
+#endif
+template <int BLOCK, bool SKIP>
+__device__ RB_RHS_LINKAGE double rhs_eval(uint32_t ent, uint32_t park, uint32_t kdst, double x, double y, double z, double vx,
+                                        double vy, double vz) {
+    const double *e = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)ent));
+    const double r[3] = {x, y, z}, v[3] = {vx, vy, vz};
+    const double *bcp = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)(park + 6u * BLOCK * 8u)));
+    double a[3], alt;
+    acceleration<false, SKIP>(e, r, v, bcp, a, nullptr, &alt);
+    sts_f64(kdst, a[0]); sts_f64(kdst + BLOCK * 8, a[1]); sts_f64(kdst + 2 * BLOCK * 8, a[2]);
+    return alt;
 }
 
 template <int BLOCK, int MIN_BLOCKS, bool SKIP>
@@ -209,7 +263,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
     double *Ks = tiles + TILE_BUFFERS * TILE_DOUBLES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Ks + K_SLOTS * K_ROWS * BLOCK);
+    double *Park = Ks + K_SLOTS * K_ROWS * BLOCK;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Park + PARK_ROWS * BLOCK);
 
     const int n_live = *p.n_live;
     const int64_t i0 = (int64_t)blockIdx.x * BLOCK;
@@ -252,87 +307,93 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         if (p.area) b_area = p.area[tid];
         if (p.mass) b_mass = p.mass[tid];
     }
-    const Body body = make_body(b_cd, b_area, b_mass);
-    double g_old = event_g(y, p.event_altitude);
+    // column of this lane's samples: trajectory index (dense rows) or position in the live list (packed slabs; the
+    // host passes `samples` biased so that row k of the run is at samples + k * sample_stride in both modes).
+    // Recomputed where it is used (sample steps, retirement) rather than carried in registers through the stages.
+#define RB_SAMPLE_COL() (p.packed ? (int64_t)blockIdx.x * BLOCK + threadIdx.x : (int64_t)tid)
+    if (p.packed) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && p.slab_live) *p.slab_live = n_live;
+        // a listed lane that is already retired (only without compaction) owns columns nobody else writes
+        if (!alive && i < n_live && p.samples) nan_rows(p, RB_SAMPLE_COL(), p.k_first, p.k_last);
+    }
+    // 32-bit shared addresses of this thread's columns, kept opaque so that they live in ONE register each instead of
+    // being rebuilt (thread id, shared window base) at every use
+    uint32_t Kt = smem_u32(Ks) + threadIdx.x * 8;     // Ka of slot s, component c at Kt + (s*3 + c)*BLOCK*8
+    asm volatile("" : "+r"(Kt));
+    const uint32_t Pk = Kt + K_SLOTS * K_ROWS * BLOCK * 8;   // parked: y_n[c] at Pk + c*BLOCK*8, bc at row 6, g_old at row 7
+    sts_f64(Pk + 6 * BLOCK * 8, make_body(b_cd, b_area, b_mass).bc);
+    sts_f64(Pk + 7 * BLOCK * 8, event_g(y, p.event_altitude));
     __syncthreads();  // barrier init visible to all before anyone waits
 
-    uint32_t Kt = smem_u32(Ks) + threadIdx.x * 8;   // shared address of Ka slot 0, component 0 of this thread:
-    asm volatile("" : "+r"(Kt));                    // Ka of slot s, component c at Kt + (s*3 + c)*BLOCK*8; opaque, so
-                                                    // that it stays in a register instead of being rebuilt per use
-    int k0 = 0;                     // slot currently holding Ka_0 (toggles 0 <-> 6, FSAL without a copy)
-    int to_sample = (int)(p.out_stride - (p.run_step0 % p.out_stride));  // steps until the next stored sample
-    int64_t next_k = p.run_step0 / p.out_stride + 1;
-    double ys[6];   // stage state; equals y_n for the launch's very first evaluation (s == 0)
-#pragma unroll
-    for (int c = 0; c < 6; ++c) ys[c] = y[c];
-    for (int t = 0; t < n_tiles; ++t) {
+    int to_sample = (int)(p.k_first * p.out_stride - p.run_step0);  // steps until the next stored sample
+    int64_t next_k = p.k_first;
+    int t = 0;
+    for (; t < n_tiles; ++t) {
         mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
-        const double *tile = tiles + (t % TILE_BUFFERS) * TILE_DOUBLES;
+        uint32_t ent = smem_u32(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES);   // entry 5 m of the tile = t_n of its step m
         const int ts = tile_steps_of(t);
-        // stage loop flattened so that the acceleration code exists ONCE in the kernel:
-        // s = 0 only for the very first evaluation of the launch (Ka_0 = a(t_n, y_n)).
-        int m = 0;
-        int s = (t == 0) ? 0 : 1;
-        const double *ent = tile + s * HOT_DOUBLES;   // entry 5 m + min(s, 5) of the tile, advanced with the stage
-        while (m < ts) {
+        // the launch's very first evaluation: Ka_0 = a(t_n, y_n) (later steps inherit it from the previous step: FSAL)
+        if (t == 0 && alive) rhs_eval<BLOCK, SKIP>(ent, Pk, Kt, y[0], y[1], y[2], y[3], y[4], y[5]);
+        for (int m = 0; m < ts; ++m) {
             if (alive) {
-                switch (s) {
-                    case 0: break;   // ys = y_n: set before the loop
-                    case 1: stage_state<1, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 2: stage_state<2, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 3: stage_state<3, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 4: stage_state<4, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    case 5: stage_state<5, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                    default: stage_state<6, BLOCK>(Kt, k0, y, p.ht, ys); break;
-                }
-                const int slot_s = (s == 6) ? (6 - k0) : s;   // (s == 0 happens only while k0 == 0)
-                double a[3], alt_new;   // alt_new = |r_s| - R of the evaluated stage state
-                acceleration<false, SKIP>(ent, ys, ys + 3, body, a, nullptr, &alt_new);
-                const uint32_t ksl = Kt + (uint32_t)((slot_s * K_ROWS) * BLOCK * 8);
-                sts_f64(ksl, a[0]); sts_f64(ksl + BLOCK * 8, a[1]); sts_f64(ksl + 2 * BLOCK * 8, a[2]);
-                if (s == 6) {
-                    // step complete: ys = y_{n+1}; the event function is the altitude the FSAL evaluation just used
-                    const double g_new = alt_new - p.event_altitude;
-                    const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
-                    // non-finite detection on the exponent bits of |r| - R (|r|^2 = inf or NaN makes it NaN; a
-                    // NaN/Inf velocity reaches r one step later; the FP64 pipe is the bottleneck, integer compares are free)
-                    const bool finite = (__double2hiint(alt_new) & 0x7ff00000) != 0x7ff00000;
-                    if (!finite) {
-                        alive = false;
-                        p.status[tid] = RB_TRAJ_NONFINITE;
-                        if (p.impact_step) p.impact_step[tid] = (int32_t)step_abs;
-                    } else if (g_old >= 0.0 && g_new <= 0.0) {  // scipy ivp.py:151, direction -1
-                        alive = false;                          // y keeps y_n for the refinement kernel
-                        p.status[tid] = RB_TRAJ_IMPACTED;
-                        if (p.impact_step) p.impact_step[tid] = (int32_t)step_abs;
-                    } else {
+                constexpr uint32_t EB = HOT_DOUBLES * 8, SB = K_ROWS * BLOCK * 8;   // bytes per table entry / per K slot
+                double ys[6];
+                stage_state<1, BLOCK>(Kt, y, p.ht, ys);
+                rhs_eval<BLOCK, SKIP>(ent + 1 * EB, Pk, Kt + 1 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
+                stage_state<2, BLOCK>(Kt, y, p.ht, ys);
+                rhs_eval<BLOCK, SKIP>(ent + 2 * EB, Pk, Kt + 2 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
+                stage_state<3, BLOCK>(Kt, y, p.ht, ys);
+                rhs_eval<BLOCK, SKIP>(ent + 3 * EB, Pk, Kt + 3 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
+                stage_state<4, BLOCK>(Kt, y, p.ht, ys);
+                rhs_eval<BLOCK, SKIP>(ent + 4 * EB, Pk, Kt + 4 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
+                stage_state<5, BLOCK>(Kt, y, p.ht, ys);
+                rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt + 5 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
+                // the step's end point (stage 6; row 6 of A = B).  y_n is parked in shared memory, y becomes y_{n+1},
+                // and its evaluation (at t_{n+1}, the entry of stage 5) is the next step's Ka_0 (slot 0: every Ka of this
+                // step has been consumed by then).  The event function is the altitude that evaluation returns.
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) y[c] = ys[c];
-                        g_old = g_new;
-                        if (to_sample == 1 && p.samples) {
-                            double *sp = p.samples + next_k * p.sample_stride + tid;
+                for (int c = 0; c < 6; ++c) sts_f64(Pk + c * BLOCK * 8, y[c]);
+                stage_state<6, BLOCK>(Kt, y, p.ht, ys);
 #pragma unroll
-                            for (int c = 0; c < 6; ++c) st_stream(sp + c * p.field_stride, ys[c]);
-                            st_stream(sp + 6 * p.field_stride, alt_new);
-                            const double v2 = fma(ys[5], ys[5], fma(ys[3], ys[3], ys[4] * ys[4]));
-                            st_stream(sp + 7 * p.field_stride, sqrt(v2));
+                for (int c = 0; c < 6; ++c) y[c] = ys[c];
+                const double alt_new = rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt, y[0], y[1], y[2], y[3], y[4], y[5]);
+                const double g_new = alt_new - p.event_altitude;
+                const double g_old = lds_f64(Pk + 7 * BLOCK * 8);
+                const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
+                // non-finite detection on the exponent bits of |r| - R (|r|^2 = inf or NaN makes it NaN; a
+                // NaN/Inf velocity reaches r one step later; the FP64 pipe is the bottleneck, integer compares are free)
+                const bool finite = (__double2hiint(alt_new) & 0x7ff00000) != 0x7ff00000;
+                const bool hit = g_old >= 0.0 && g_new <= 0.0;   // scipy ivp.py:151, direction -1
+                if (!finite || hit) {
+                    alive = false;
+                    p.status[tid] = finite ? RB_TRAJ_IMPACTED : RB_TRAJ_NONFINITE;
+                    if (p.impact_step) p.impact_step[tid] = (int32_t)step_abs;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) y[c] = lds_f64(Pk + c * BLOCK * 8);   // y_n: where k_refine restarts the step
+                    if (p.packed && p.samples) {
+                        // (k_refine stores the sample of a grid time that coincides with the event time: where)
+                        if (finite && to_sample == 1) {
+                            p.edge_slot[2 * (int64_t)tid] = p.slab_offset + (next_k - p.sample_row0) * p.sample_stride + RB_SAMPLE_COL();
+                            p.edge_slot[2 * (int64_t)tid + 1] = p.field_stride;
                         }
+                        nan_rows(p, RB_SAMPLE_COL(), next_k, p.k_last);
+                    }
+                } else {
+                    sts_f64(Pk + 7 * BLOCK * 8, g_new);
+                    if (to_sample == 1 && p.samples) {
+                        double *sp = p.samples + next_k * p.sample_stride + RB_SAMPLE_COL();
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) st_stream(sp + c * p.field_stride, y[c]);
+                        st_stream(sp + 6 * p.field_stride, alt_new);
+                        const double v2 = fma(y[5], y[5], fma(y[3], y[3], y[4] * y[4]));
+                        st_stream(sp + 7 * p.field_stride, sqrt(v2));
                     }
                 }
             }
-            if (s == 6) {
-                k0 = 6 - k0;
-                ++m;
-                s = 1;
-                ent += HOT_DOUBLES;
-                if (--to_sample == 0) { to_sample = (int)p.out_stride; ++next_k; }
-                // warp-ballot retirement: a warp with no live lane leaves (warp 0 stays while
-                // tiles remain to be issued)
-                if (!__any_sync(0xffffffffu, alive) && (threadIdx.x >= 32 || t + TILE_BUFFERS >= n_tiles)) goto done;
-            } else {
-                ++s;
-                if (s != 6) ent += HOT_DOUBLES;   // stage 6 is evaluated at t_{n+1}, the entry of stage 5
-            }
+            ent += RB_STAGES_PER_STEP * HOT_DOUBLES * 8;
+            if (--to_sample == 0) { to_sample = (int)p.out_stride; ++next_k; }
+            // warp-ballot retirement: a warp with no live lane leaves (warp 0 stays while tiles remain to be issued)
+            if (!__any_sync(0xffffffffu, alive) && (threadIdx.x >= 32 || t + TILE_BUFFERS >= n_tiles)) goto done;
         }
         if (t + TILE_BUFFERS < n_tiles) {
             __syncthreads();  // everyone is done reading this tile's buffer
@@ -340,10 +401,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         }
     }
 done:
+    // (left through the warp vote) a tile issued ahead but not consumed must land before the block's shared memory is
+    // released: the bulk copy and its mbarrier complete_tx would otherwise hit whatever block the SM schedules next
+    if (TILE_BUFFERS > 1 && threadIdx.x == 0 && t + 1 < n_tiles) mbar_wait(&bars[(t + 1) % TILE_BUFFERS], (uint32_t)(((t + 1) / TILE_BUFFERS) & 1));
     if (loaded) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) p.state[c * p.n + tid] = y[c];
     }
+#undef RB_SAMPLE_COL
 }
 
 // ---------------------------------------------------------------- compaction of the live list
@@ -456,6 +521,7 @@ struct RefineParams {
     int64_t run_first_step, run_n_steps;
     int refine;
     int32_t *edge_count;
+    const int64_t *edge_slot;   // packed sample slabs: `samples` is the arena, the row's place comes from the step kernel
 };
 
 struct Dense {
@@ -576,9 +642,11 @@ __global__ void __launch_bounds__(128) k_refine(const RefineParams p) {
         if (te >= t_new && (local_new % p.out_stride) == 0) {
             if (p.samples) {
                 double *sp = p.samples + (local_new / p.out_stride) * p.sample_stride + tid;
-                for (int c = 0; c < 6; ++c) sp[c * p.field_stride] = ys[c];
-                sp[6 * p.field_stride] = event_g(ys, 0.0);
-                sp[7 * p.field_stride] = sqrt(ys[3] * ys[3] + ys[4] * ys[4] + ys[5] * ys[5]);
+                int64_t fs = p.field_stride;
+                if (p.edge_slot) { sp = p.samples + p.edge_slot[2 * tid]; fs = p.edge_slot[2 * tid + 1]; }
+                for (int c = 0; c < 6; ++c) sp[c * fs] = ys[c];
+                sp[6 * fs] = event_g(ys, 0.0);
+                sp[7 * fs] = sqrt(ys[3] * ys[3] + ys[4] * ys[4] + ys[5] * ys[5]);
             }
             ns += 1;
             if (p.edge_count) atomicAdd(p.edge_count, 1);

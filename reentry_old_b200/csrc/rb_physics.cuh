@@ -111,6 +111,15 @@ static const Consts h_k = RB_CONSTS_INIT;
 struct Body {  // per-trajectory constant bc = 0.5 Cd A / m (SpacecraftModel.Cd / .A / .m, spacecraft_model.py:394-397, :204-206)
     double bc;
 };
+struct RhsOut;
+template <bool DIAG, bool SKIP = false>
+RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const double *bcp,
+                        double a[3], RhsOut *diag, double *altitude_out = nullptr);
+template <bool DIAG, bool SKIP = false>
+RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
+                        double a[3], RhsOut *diag, double *altitude_out = nullptr) {
+    acceleration<DIAG, SKIP>(e, r, v, &b.bc, a, diag, altitude_out);
+}
 RB_HD Body make_body(double cd, double area, double mass) { return Body{0.5 * cd * area / mass}; }
 
 struct RhsOut {  // optional diagnostics (dict of spacecraft_model.py:472-480)
@@ -290,9 +299,11 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
     return (c0 * rb_exp_bounded(arg)) * (latitude_factor * factor);
 #undef RB_ALT_GE
 }
-template <bool DIAG, bool SKIP = false>
-RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
-                        double a[3], RhsOut *diag, double *altitude_out = nullptr) {
+// bcp: where the body constant bc = Cd A / (2 m) is read from AT ITS USE (the very end of the evaluation): the step
+// kernel parks it in shared memory instead of holding two registers through the whole evaluation.
+template <bool DIAG, bool SKIP>
+RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const double *bcp,
+                        double a[3], RhsOut *diag, double *altitude_out) {
     const double x = r[0], y = r[1], z = r[2];
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
@@ -374,7 +385,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         }
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
         const double vn = w2 * rb_rsqrt(w2);
-        const double kd = -(rho * b.bc) * vn;
+        const double kd = -(rho * *bcp) * vn;
         if (DIAG) {
             const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;
             diag->a_drag[0] = ddx; diag->a_drag[1] = ddy; diag->a_drag[2] = ddz;

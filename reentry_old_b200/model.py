@@ -76,8 +76,11 @@ class DeviceContext:
 
     # -- time table -------------------------------------------------------------------
     def stage_time_table(self, epoch_jd, gmst0, t0, dt, n_steps, stream_ptr, n_threads=0):
+        # the C context is the source of truth: its generation counter changes whenever anything (this method, a
+        # *_host call, another binding) restages the table, and the cached key is only trusted while it has not
         key = (float(epoch_jd), float(gmst0), float(t0), float(dt))
-        if self.table_key is not None and self.table_key[:4] == key and self.table_key[4] >= n_steps:
+        gen = self.lib.rb_ctx_table_generation(self.handle)
+        if self.table_key is not None and self.table_key[:4] == key and self.table_key[4] >= n_steps and self.table_key[5] == gen:
             return
         torch = _torch()
         n_entries = self.lib.rb_time_table_entries(n_steps)
@@ -87,7 +90,7 @@ class DeviceContext:
         self.check(self.lib.rb_ctx_set_time_table(self.handle, host.data_ptr(), n_steps, t0, dt, stream_ptr),
                    "rb_ctx_set_time_table")
         torch.cuda.current_stream(self.device).synchronize()  # pinned staging buffer is released below
-        self.table_key = key + (int(n_steps),)
+        self.table_key = key + (int(n_steps), self.lib.rb_ctx_table_generation(self.handle))
 
     def stats(self):
         s = L.RbStats()
@@ -104,6 +107,92 @@ class DeviceContext:
         return out.value
 
 
+class PackedSamples:
+    """Samples as PACKED SLABS (include/reentry_b200.h, rb_sample_slab): the rows each launch wrote, only as wide as
+    the ensemble that was still alive.  `arena` is a flat float64 tensor (device, or pinned host memory for the host
+    path), `slabs` a list of dicts.  Column j of a slab is the j-th trajectory (ascending index) of its partition with
+    impact_step == -1 or > first_step: the column map is derived from the summaries, no index array is stored."""
+
+    def __init__(self, arena, slabs, impact_step, status, n_samples, n, n_out):
+        self.arena, self.slabs, self.n, self.n_out = arena, slabs, int(n), int(n_out)
+        self.impact_step, self.status, self.n_samples = impact_step, status, n_samples
+
+    @staticmethod
+    def slabs_from_ctypes(arr, count):
+        return [dict(offset=a.offset, first_row=a.first_row, n_rows=a.n_rows, first_traj=a.first_traj, n_traj=a.n_traj,
+                     width=a.width, first_step=a.first_step, n_live=a.n_live) for a in arr[:count]]
+
+    @property
+    def used(self):     # doubles of the arena in use
+        return max((s["offset"] + s["n_rows"] * L.RB_SAMPLE_FIELDS * s["width"] for s in self.slabs), default=0)
+
+    def _resolve_live(self):
+        # rb_propagate is asynchronous: its host descriptors carry n_live = -1 and the counts sit in a device array
+        sl = getattr(self, "slab_live", None)
+        if sl is not None and any(s["n_live"] < 0 for s in self.slabs):
+            live = sl.cpu().tolist()
+            for i, s in enumerate(self.slabs):
+                if s["n_live"] < 0:
+                    s["n_live"] = int(live[i])
+
+    def columns(self, slab):
+        """Trajectory indices of the slab's columns (tensor on the device of impact_step)."""
+        import torch
+
+        self._resolve_live()
+        a, b = slab["first_traj"], slab["first_traj"] + slab["n_traj"]
+        if slab["n_live"] == slab["n_traj"]:   # nothing retired yet -- or a run without compaction, whose list never shrinks
+            return torch.arange(a, b, device=self.impact_step.device)
+        keep = (self.status[a:b] == L.TRAJ_ALIVE) | (self.impact_step[a:b] > slab["first_step"])
+        return torch.nonzero(keep, as_tuple=False).flatten() + a
+
+    def view(self, slab):
+        """[n_rows, 8, width] view of the slab in the arena."""
+        sz = slab["n_rows"] * L.RB_SAMPLE_FIELDS * slab["width"]
+        return self.arena[slab["offset"]: slab["offset"] + sz].view(slab["n_rows"], L.RB_SAMPLE_FIELDS, slab["width"])
+
+    def row(self, k):
+        """Sample k of the ensemble: (trajectory indices [m], values [8, m]) of the trajectories alive at the launch
+        that wrote the row (entries of a trajectory that retired inside that launch before step k*out_stride are NaN)."""
+        import torch
+
+        ids, vals = [], []
+        for s in self.slabs:
+            if s["first_row"] <= k < s["first_row"] + s["n_rows"]:
+                c = self.columns(s)
+                ids.append(c)
+                vals.append(self.view(s)[k - s["first_row"], :, : c.numel()].to(c.device))
+        if not ids:
+            raise IndexError(k)
+        return torch.cat(ids), torch.cat(vals, dim=1)
+
+    def to_dense(self, n_out=None):
+        """[n_out, 8, N] with NaN wherever there is no valid sample (the layout of non-packed runs)."""
+        import torch
+
+        n_out = self.n_out if n_out is None else int(n_out)
+        dense = torch.full((n_out, L.RB_SAMPLE_FIELDS, self.n), float("nan"), dtype=torch.float64, device=self.arena.device)
+        for s in self.slabs:
+            c = self.columns(s).to(self.arena.device)
+            dense[s["first_row"]: s["first_row"] + s["n_rows"], :, c] = self.view(s)[:, :, : c.numel()]
+        return dense
+
+    def trajectory(self, i):
+        """[n_samples_i, 8] samples of trajectory i."""
+        import torch
+
+        out = []
+        for s in self.slabs:
+            if s["first_traj"] <= i < s["first_traj"] + s["n_traj"]:
+                c = self.columns(s)
+                j = torch.searchsorted(c, torch.tensor([i], device=c.device))
+                if j.item() < c.numel() and c[j].item() == i:
+                    out.append((s["first_row"], self.view(s)[:, :, j.item()]))
+        out.sort(key=lambda t: t[0])
+        rows = torch.cat([v for _, v in out], dim=0) if out else torch.empty((0, L.RB_SAMPLE_FIELDS), dtype=torch.float64)
+        return rows[: int(self.n_samples[i])]
+
+
 @dataclass
 class EnsembleResult:
     """Device-resident result of `run_ensemble` (torch tensors on the GPU unless noted)."""
@@ -118,6 +207,7 @@ class EnsembleResult:
     out_stride: int = 1
     n_steps: int = 0
     stats: dict = field(default_factory=dict)
+    packed: Optional[PackedSamples] = None   # run_ensemble(..., samples="packed"): `samples` is then None
 
     @property
     def y(self):          # [N, 6, n_out] view (sol.y of trajectory i is y[i])
@@ -274,11 +364,16 @@ class SpacecraftModel:
     # ------------------------------------------------------------------- run_ensemble
     def run_ensemble(self, y0, t0=0.0, dt=1.0, n_steps=0, out_stride=1, Cd=None, A=None, m=None,
                      store_samples=True, steps_per_launch=0, compact=True, early_exit=True, refine=True,
-                     event_altitude=1000.0, table_threads=0, profile=False, skip_negligible_drag=False, overlap=True) -> EnsembleResult:
+                     event_altitude=1000.0, table_threads=0, profile=False, skip_negligible_drag=False, overlap=True,
+                     samples="dense", packed_capacity=None) -> EnsembleResult:
         """Propagate N independent initial states y0[N,6] for up to n_steps fixed steps of dt.
 
         Per-trajectory Cd / A / m may be given as arrays [N]; otherwise the model's scalars apply.
-        Samples are stored every `out_stride` steps as [n_out, 8, N] (SoA, coalesced).
+        Samples are stored every `out_stride` steps: samples="dense" as [n_out, 8, N] (SoA, coalesced, NaN after a
+        trajectory's event); samples="packed" as slabs only as wide as the live ensemble (`result.packed`,
+        PackedSamples) -- what a run "until impact" with a generous step cap should use: nothing is allocated,
+        filled or written for the part of the cap the ensemble never flies.  packed_capacity (doubles of the arena)
+        defaults to the dense size, the worst case; pass what the run needs when the cap is generous.
         """
         torch = _torch()
         ctx = self._ctx()
@@ -298,8 +393,20 @@ class SpacecraftModel:
         stream = torch.cuda.current_stream(ctx.device).cuda_stream
         ctx.stage_time_table(self.epoch, self.gmst0, float(t0), float(dt), int(n_steps), stream, table_threads)
         n_out = n_steps // out_stride + 1
+        if samples not in ("dense", "packed"):
+            raise ValueError("samples must be 'dense' or 'packed'")
+        packed = store_samples and samples == "packed"
         samples = torch.full((n_out, L.RB_SAMPLE_FIELDS, n), float("nan"), dtype=torch.float64, device=dev) \
-            if store_samples else None
+            if store_samples and not packed else None
+        arena = slabs = slab_live = None
+        n_slabs = C.c_int64(0)
+        if packed:
+            spl = int(steps_per_launch) if steps_per_launch > 0 else 32
+            slab_cap = 2 * (n_steps // spl + 2) + 1
+            cap = int(packed_capacity) if packed_capacity else n_out * L.RB_SAMPLE_FIELDS * ((n + 15) // 16 * 16 + 16)
+            arena = torch.empty(cap, dtype=torch.float64, device=dev)
+            slabs = (L.RbSampleSlab * slab_cap)()
+            slab_live = torch.zeros(slab_cap, dtype=torch.int32, device=dev)
         final_state = torch.empty((6, n), dtype=torch.float64, device=dev)
         impact_step = torch.empty(n, dtype=torch.int32, device=dev)
         impact_time = torch.empty(n, dtype=torch.float64, device=dev)
@@ -313,19 +420,75 @@ class SpacecraftModel:
                      cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
         flags = (L.RB_FLAG_COMPACT if compact else 0) | (L.RB_FLAG_EARLY_EXIT if early_exit else 0) | \
                 (0 if refine else L.RB_FLAG_NO_REFINE) | (L.RB_FLAG_PROFILE if profile else 0) | \
-                (L.RB_FLAG_SKIP_NEGLIGIBLE_DRAG if skip_negligible_drag else 0) | (0 if overlap else L.RB_FLAG_NO_OVERLAP)
+                (L.RB_FLAG_SKIP_NEGLIGIBLE_DRAG if skip_negligible_drag else 0) | (0 if overlap else L.RB_FLAG_NO_OVERLAP) | \
+                (L.RB_FLAG_PACKED_SAMPLES if packed else 0)
         run = L.RbRun(first_step=0, n_steps=int(n_steps), out_stride=int(out_stride),
                       steps_per_launch=int(steps_per_launch), event_altitude=float(event_altitude), flags=flags)
-        out = L.RbOut(samples=None if samples is None else samples.data_ptr(),
+        out = L.RbOut(samples=(arena.data_ptr() if packed else None if samples is None else samples.data_ptr()),
                       sample_stride=L.RB_SAMPLE_FIELDS * n, field_stride=n, n_out_capacity=n_out,
                       final_state=final_state.data_ptr(), impact_step=impact_step.data_ptr(),
-                      impact_time=impact_time.data_ptr(), status=status.data_ptr(), n_samples=n_samples.data_ptr())
+                      impact_time=impact_time.data_ptr(), status=status.data_ptr(), n_samples=n_samples.data_ptr(),
+                      packed_capacity=(arena.numel() if packed else 0), slabs=slabs if packed else None,
+                      slab_capacity=(len(slabs) if packed else 0), n_slabs=C.pointer(n_slabs) if packed else None,
+                      slab_live=slab_live.data_ptr() if packed else None)
         if n > 0:
             ctx.check(ctx.lib.rb_propagate(ctx.handle, C.byref(rin), C.byref(run), C.byref(out), stream), "rb_propagate")
         t = float(t0) + float(dt) * out_stride * np.arange(n_out)
+        pk = None
+        if packed:
+            pk = PackedSamples(arena, PackedSamples.slabs_from_ctypes(slabs, n_slabs.value), impact_step, status, n_samples, n, n_out)
+            pk.slab_live = slab_live   # device [n_slabs]: live count of every slab (n_live = -1 in the host descriptors)
         return EnsembleResult(t=t, samples=samples, final_state=final_state, impact_step=impact_step,
                               impact_time=impact_time, status=status, n_samples=n_samples, dt=float(dt),
-                              out_stride=int(out_stride), n_steps=int(n_steps), stats=ctx.stats())
+                              out_stride=int(out_stride), n_steps=int(n_steps), stats=ctx.stats(), packed=pk)
+
+    # ------------------------------------------------------------- host-buffer path
+    def host_buffers(self, n, n_steps, out_stride, packed_capacity, steps_per_launch=0):
+        """Pinned host buffers for run_ensemble_host (allocate once, reuse for every batch of the same shape)."""
+        torch = _torch()
+        spl = int(steps_per_launch) if steps_per_launch > 0 else 32
+        b = dict(n=int(n), n_steps=int(n_steps), out_stride=int(out_stride), steps_per_launch=int(steps_per_launch))
+        b["y0"] = torch.empty((n, 6), dtype=torch.float64).pin_memory()
+        b["packed"] = torch.empty(int(packed_capacity), dtype=torch.float64).pin_memory() if packed_capacity else None
+        b["slabs"] = (L.RbSampleSlab * (2 * (n_steps // spl + 2) + 1))()
+        b["final_state"] = torch.empty((n, 6), dtype=torch.float64).pin_memory()
+        b["impact_step"] = torch.empty(n, dtype=torch.int32).pin_memory()
+        b["impact_time"] = torch.empty(n, dtype=torch.float64).pin_memory()
+        b["status"] = torch.empty(n, dtype=torch.uint8).pin_memory()
+        b["n_samples"] = torch.empty(n, dtype=torch.int32).pin_memory()
+        return b
+
+    def run_ensemble_host(self, buffers, t0=0.0, dt=1.0, event_altitude=1000.0) -> EnsembleResult:
+        """End to end with HOST memory: buffers["y0"] [N,6] in, everything else out (host tensors in `buffers`).  One
+        call = upload of the initial states, time table built chunk-wise on the host while the GPU runs, propagation
+        until impact (cap n_steps), every packed sample slab sent by ONE copy-engine transfer as soon as its launch
+        finished, summaries; returns when all of it is in host memory.  Samples come back packed (result.packed, host
+        arena); buffers["packed"] = None propagates without samples."""
+        ctx = self._ctx()
+        if self.sim_type != "RK45":
+            raise NotImplementedError("only the RK45 (Dormand-Prince) tableau is implemented on this path")
+        b = buffers
+        n, n_steps, out_stride = b["n"], b["n_steps"], b["out_stride"]
+        run = L.RbRun(first_step=0, n_steps=n_steps, out_stride=out_stride, steps_per_launch=b["steps_per_launch"],
+                      event_altitude=float(event_altitude), flags=0)
+        n_slabs, used = C.c_int64(0), C.c_int64(0)
+        pk = b["packed"]
+        rc = ctx.lib.rb_propagate_host_packed(
+            ctx.handle, n, b["y0"].data_ptr(), None, None, None, float(self.Cd), float(self.A), float(self.m), self.epoch,
+            self.gmst0, float(t0), float(dt), C.byref(run), pk.data_ptr() if pk is not None else None,
+            pk.numel() if pk is not None else 0, b["slabs"], len(b["slabs"]), C.byref(n_slabs), C.byref(used),
+            b["final_state"].data_ptr(), b["impact_step"].data_ptr(), b["impact_time"].data_ptr(), b["status"].data_ptr(),
+            b["n_samples"].data_ptr())
+        ctx.check(rc, "rb_propagate_host_packed")
+        n_out = n_steps // out_stride + 1
+        packed = None
+        if pk is not None:
+            packed = PackedSamples(pk, PackedSamples.slabs_from_ctypes(b["slabs"], n_slabs.value), b["impact_step"], b["status"],
+                                   b["n_samples"], n, n_out)
+        return EnsembleResult(t=float(t0) + float(dt) * out_stride * np.arange(n_out), samples=None,
+                              final_state=b["final_state"].t(), impact_step=b["impact_step"], impact_time=b["impact_time"],
+                              status=b["status"], n_samples=b["n_samples"], dt=float(dt), out_stride=out_stride,
+                              n_steps=n_steps, stats=ctx.stats(), packed=packed)
 
     # ------------------------------------------------------------- ground track (N2)
     def ground_track(self, res: EnsembleResult, threshold=100000.0, t0=0.0):

@@ -144,12 +144,14 @@ def test_golden_reentry(Model, golden_dir, name):
     assert np.allclose(s[ok][:, 7], np.linalg.norm(s[ok][:, 3:6], axis=1), rtol=1e-15)
 
 
-@pytest.mark.parametrize("name", ["c3_sso.npz", "c4_geo_heo.npz"])
+@pytest.mark.parametrize("name", ["c3_sso.npz", "c4_geo_heo.npz", "c3_sso_7d.npz", "c4_geo_heo_30d.npz"])
 def test_golden_orbits(Model, golden_dir, name):
-    """Compared horizon: 1 day (C3) / 6 days (C4), strict."""
+    """Compared horizon, strict bars: 1 day x 8 and 7 days x 64 satellites (C3), 6 days x 8 and 30 days x 64 (C4);
+    every golden is the output of the unmodified reference's functions (oracle/make_golden.py)."""
     g = np.load(os.path.join(golden_dir, name))
     res = run_golden(Model, g, steps_per_launch=1024)
-    compare_states(samples_np(res)[:, :, :6], g["ys"], name)
+    rel, relv = compare_states(samples_np(res)[:, :, :6], g["ys"], name)
+    print(f"{name}: max rel position {rel:.2e}, velocity {relv:.2e}")
     assert np.all(res.impact_step.cpu().numpy() == -1) and np.all(res.status.cpu().numpy() == 0)
 
 
@@ -319,7 +321,6 @@ def test_propagate_host_matches_device_path(Model, torch):
                                    0.0, 0.5, C.byref(run), samples.ctypes.data, n_out, fs.ctypes.data, istep.ctypes.data,
                                    itime.ctypes.data, st.ctypes.data, ns.ctypes.data, C.byref(used))
     assert rc == 0, ctx.lib.rb_ctx_last_error(ctx.handle)
-    ctx.table_key = None  # the host call staged its own table
     assert np.array_equal(istep, r.impact_step.cpu().numpy()) and np.array_equal(st, r.status.cpu().numpy())
     assert np.array_equal(itime, r.impact_time.cpu().numpy()) and np.array_equal(ns, r.n_samples.cpu().numpy())
     assert np.array_equal(fs, r.final_state.t().cpu().numpy())
@@ -356,7 +357,6 @@ def test_propagate_host_zero_copy_samples(Model, torch):
                                        0.5, C.byref(run), samples.data_ptr(), n_out, fs.data_ptr(), ist.data_ptr(), it.data_ptr(),
                                        st.data_ptr(), ns.data_ptr(), C.byref(used))
         assert rc == 0, ctx.lib.rb_ctx_last_error(ctx.handle)
-        ctx.table_key = None
         k = used.value
         ref = r.samples[:k].cpu()
         valid = ~torch.isnan(ref)

@@ -185,7 +185,8 @@ def test_reentry_ensembles(oracle, golden_dir, name):
         assert r["impact_step"][2] != r["impact_step"][3]            # Cd/A/m are per trajectory
 
 
-@pytest.mark.parametrize("name,tol", [("c3_sso.npz", 1e-11), ("c4_geo_heo.npz", 1e-11)])
+@pytest.mark.parametrize("name,tol", [("c3_sso.npz", 1e-11), ("c4_geo_heo.npz", 1e-11),
+                                      ("c3_sso_7d.npz", 1e-10), ("c4_geo_heo_30d.npz", 1e-10)])
 def test_orbit_ensembles(oracle, golden_dir, name, tol):
     O = oracle
     g = load(golden_dir, name)

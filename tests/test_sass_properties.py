@@ -1,7 +1,10 @@
 """Static properties of the built sm_100a step kernel (no GPU needed: cuobjdump reads the in-tree library).
 Guards the design points DESIGN.md 5.1 relies on: TMA bulk copies + mbarrier for the time-table tiles, register
-budget for 6 resident blocks per SM, FP64 seeds from MUFU, shared-memory K rows through immediate-offset LDS, and
-the instruction budget of the hot loop."""
+budget for 6 resident blocks per SM, FP64 seeds from MUFU, shared-memory K rows through immediate-offset LDS, the
+instruction budget of the hot loop -- and that the FP64 instruction mix is the one the roofline's flop-per-step
+calibration (profiles/flop_per_traj_step.json) was measured on."""
+import json
+import os
 import re
 import shutil
 import subprocess
