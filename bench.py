@@ -197,24 +197,43 @@ def cpu_baseline_block(w, seconds=12.0):
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on the box's host cores: oracle/_ref (the reference's numba
+    functions, compiled from /root/reference by oracle/build_ref.py) when it is there, else the C port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = workload(args.n_traj, 0)
     per_step_seconds = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    vals, threads, sample = [], 1, ""
+    use_ref = False
+    try:
+        from oracle import ref_native
+        use_ref = ref_native.available()
+    except Exception:
+        use_ref = False
+    vals, cores, sample, per_core = [], 1, "", None
     for k in range(args.warmup + args.steps):
-        rate, threads, sample, steps, el = cpu_oracle_rate(w, per_step_seconds)
+        if use_ref:
+            r = ref_native.rate(w, per_step_seconds)
+            steps = int(r["sample"].split(", ")[1].split()[0])
+            el = steps / r["value"]
+            cores, sample, per_core = r["cores"], r["sample"], r["per_core"]
+        else:
+            _, cores, sample, steps, el = cpu_oracle_rate(w, per_step_seconds)
         if k >= args.warmup:
             vals.append((steps, el))
     tot_steps = sum(s for s, _ in vals)
     tot_t = sum(e for _, e in vals)
     v = tot_steps / tot_t
-    cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "per_core": v / max(1, threads),
-           "sample": "each step: " + sample + " (C port of the reference's numba path, OpenMP over trajectories)"}
-    nb = cpu_numba_rate(w, 10.0)
-    if nb is not None:
-        cpu["reference_numba"] = nb
+    if use_ref:
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "per_core": per_core,
+               "sample": "each step: " + sample + " (the reference's own numba-compiled functions, oracle/_ref, under the "
+                                                  "fixed-step Dormand-Prince driver; one process per core)"}
+        rate, threads, psample, _, _ = cpu_oracle_rate(w, 6.0)
+        cpu["port"] = {"value": rate, "cores": threads, "per_core": rate / max(1, threads), "kind": "port", "sample": psample}
+    else:
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "per_core": v / max(1, cores),
+               "sample": "each step: " + sample + " (C port of the reference's numba path, OpenMP over trajectories; "
+                                                  "oracle/_ref was not built)"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -9,7 +9,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -818,56 +820,69 @@ struct EventSet {   // events of one call, destroyed on every exit path
     ~EventSet() { for (auto e : evs) cudaEventDestroy(e); }
 };
 
-// The step kernel's table (96-byte entries) built on the HOST in chunks while the GPU already runs, and only as
-// far as launches are actually enqueued: a run "until impact" with a generous step cap pays for the steps it flies.
+// The step kernel's table (96-byte entries) is built on the HOST while the GPU already runs, and only as far as
+// launches are actually enqueued: a run "until impact" with a generous step cap pays for the steps it flies.  ONE
+// builder thread per call (no OpenMP team: eight ranks of a box share its cores, and a team that has to be woken up
+// or is oversubscribed showed 4-13 ms outliers on the critical path) runs ahead of the launch loop; the launch loop
+// uploads what has been built before each launch that needs it.
 struct TableFeeder : LaunchHook {
-    rb_ctx *ctx;
-    double epoch_jd, gmst0, t0, dt;
-    int64_t n_steps, built_steps = -1;   // entries 0 .. 5 built_steps are on their way to the device
-    int64_t chunk_steps = 512;
-    std::vector<double> tn;              // t_n exactly as scipy accumulates it (t_{n+1} = t_n + dt)
-    double *h_hot;                       // pinned staging, [entries][HOT_DOUBLES]
-    cudaStream_t up_stream;
-    cudaEvent_t up_ev;
+    rb_ctx *ctx = nullptr;
+    double epoch_jd = 0, gmst0 = 0, t0 = 0, dt = 0;
+    int64_t n_steps = 0;
+    double *h_hot = nullptr;             // pinned staging, [entries][HOT_DOUBLES]
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t up_ev = nullptr;
     cudaError_t err = cudaSuccess;
-    double ms_build = 0.0;
-    int32_t before_launch(int64_t step_end, const cudaStream_t *streams, int n_streams) override {
-        if (step_end <= built_steps) return RB_OK;
-        const int64_t target = std::min(n_steps, ((step_end + chunk_steps - 1) / chunk_steps) * chunk_steps);
-        const int64_t e0 = built_steps < 0 ? 0 : RB_STAGES_PER_STEP * built_steps + 1, e1 = RB_STAGES_PER_STEP * target + 1;
-        const auto t_a = std::chrono::steady_clock::now();
-        if ((int64_t)tn.size() < target + 1) {
-            double t = tn.empty() ? t0 : tn.back();
-            if (tn.empty()) tn.push_back(t);
-            while ((int64_t)tn.size() < target + 1) { t = t + dt; tn.push_back(t); }
-        }
-        const double C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
-        const double *tnp = tn.data();
-        double *hot = h_hot;
-        const double ej = epoch_jd, g0 = gmst0, h = dt;
-#ifdef _OPENMP
-        const int n_threads = std::max(omp_get_max_threads(), std::min(omp_get_num_procs(), 16));
-#pragma omp parallel for schedule(static) num_threads(n_threads) if (e1 - e0 > 512)
-#endif
-        for (int64_t e = e0; e < e1; ++e) {
-            double te;
-            if (e == 0) te = tnp[0];
-            else {
-                const int64_t n = (e - 1) / RB_STAGES_PER_STEP;
-                const int s = (int)((e - 1) % RB_STAGES_PER_STEP) + 1;
-                te = (s == 5) ? tnp[n + 1] : tnp[n] + C[s] * h;
-            }
+    std::atomic<int64_t> built_steps{-1};   // entries 0 .. 5 built_steps are final in h_hot
+    std::atomic<int64_t> wanted_steps{0};   // the builder stays at most a lookahead beyond this
+    std::atomic<bool> stop{false};
+    int64_t uploaded_steps = -1;
+    std::thread builder;
+    double ms_waited = 0.0;
+    static constexpr int64_t LOOKAHEAD = 1024;
+
+    void start() {
+        builder = std::thread([this] {
+            const double C[6] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0};
+            double tn = t0;                       // t_n exactly as scipy accumulates it (t_{n+1} = t_n + dt)
             double ent[ENTRY_DOUBLES];
-            time_entry(te, ej, g0, ent);
-            hot_entry(ent, hot + e * HOT_DOUBLES);
-        }
-        ms_build += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+            time_entry(tn, epoch_jd, gmst0, ent);
+            hot_entry(ent, h_hot);
+            built_steps.store(0, std::memory_order_release);
+            for (int64_t n = 0; n < n_steps && !stop.load(std::memory_order_relaxed); ++n) {
+                while (n >= wanted_steps.load(std::memory_order_relaxed) + LOOKAHEAD && !stop.load(std::memory_order_relaxed))
+                    std::this_thread::yield();
+                const double tn1 = tn + dt;
+                for (int s = 1; s <= RB_STAGES_PER_STEP; ++s) {
+                    const double te = (s == 5) ? tn1 : tn + C[s] * dt;
+                    time_entry(te, epoch_jd, gmst0, ent);
+                    hot_entry(ent, h_hot + (RB_STAGES_PER_STEP * n + s) * HOT_DOUBLES);
+                }
+                tn = tn1;
+                if (((n + 1) & 15) == 0 || n + 1 == n_steps) built_steps.store(n + 1, std::memory_order_release);
+            }
+        });
+    }
+    void finish() {
+        stop.store(true);
+        if (builder.joinable()) builder.join();
+    }
+    ~TableFeeder() override { finish(); }
+
+    int32_t before_launch(int64_t step_end, const cudaStream_t *streams, int n_streams) override {
+        wanted_steps.store(step_end, std::memory_order_relaxed);
+        if (step_end <= uploaded_steps) return RB_OK;
+        const auto t_a = std::chrono::steady_clock::now();
+        int64_t have;
+        while ((have = built_steps.load(std::memory_order_acquire)) < step_end) std::this_thread::yield();
+        ms_waited += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
+        const int64_t e0 = uploaded_steps < 0 ? 0 : RB_STAGES_PER_STEP * uploaded_steps + 1, e1 = RB_STAGES_PER_STEP * have + 1;
         cudaError_t e = cudaMemcpyAsync(ctx->d_table + e0 * HOT_DOUBLES, h_hot + e0 * HOT_DOUBLES,
                                         (size_t)(e1 - e0) * HOT_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, up_stream);
         if (e == cudaSuccess) e = cudaEventRecord(up_ev, up_stream);
         for (int q = 0; q < n_streams && e == cudaSuccess; ++q) e = cudaStreamWaitEvent(streams[q], up_ev, 0);
         if (e != cudaSuccess) { err = e; return RB_ERR_CUDA; }
-        built_steps = target;
+        uploaded_steps = have;
         return RB_OK;
     }
 };
@@ -949,6 +964,7 @@ int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const
     SlabSender hook;
     hook.ctx = ctx; hook.epoch_jd = epoch_jd; hook.gmst0 = gmst0; hook.t0 = t0; hook.dt = dt; hook.n_steps = run->n_steps;
     hook.h_hot = ctx->h_table; hook.up_stream = ctx->up_stream;
+    hook.start();   // the builder thread runs ahead from here on (the upload of y0 below overlaps its first entries)
     hook.d_arena = (const double *)d_arena; hook.h_arena = packed; hook.copy_stream = ctx->copy_stream;
     CK(events.make(&hook.up_ev));
     CK(events.make(&hook.ev[0]));
@@ -978,6 +994,7 @@ int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const
     const auto t_prop = std::chrono::steady_clock::now();
     rc = propagate_impl(ctx, &in, &r2, &out, cs, &hook, &steps_done);
     const double ms_enqueue = ms_since(t_prop);
+    hook.finish();
     cudaError_t e = hook.err;
     if (rc == RB_OK && e == cudaSuccess) {
         double *d_aos = (double *)d_state + 6 * n;
@@ -1017,8 +1034,8 @@ int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const
         if (packed_used) *packed_used = ns_local ? slabs[ns_local - 1].offset + slabs[ns_local - 1].n_rows * RB_SAMPLE_FIELDS * slabs[ns_local - 1].width : 0;
     }
     if (trace)
-        fprintf(stderr, "rb_propagate_host_packed: table build %.2f ms (%lld of %lld steps), enqueue %.2f ms, total %.2f ms, %lld slabs, %.3f GB sent\n",
-                hook.ms_build, (long long)hook.built_steps, (long long)run->n_steps, ms_enqueue, ms_since(t_begin), (long long)ns_local, hook.bytes_sent * 1e-9);
+        fprintf(stderr, "rb_propagate_host_packed: waited %.2f ms for the table builder (%lld of %lld steps built), enqueue %.2f ms, total %.2f ms, %lld slabs, %.3f GB sent\n",
+                hook.ms_waited, (long long)hook.built_steps.load(), (long long)run->n_steps, ms_enqueue, ms_since(t_begin), (long long)ns_local, hook.bytes_sent * 1e-9);
     return rc;
 }
 

@@ -239,8 +239,11 @@ constexpr size_t propagate_smem_bytes() {
 //   kdst  32-bit shared address where a[0..2] go (this thread's column of the K slot)
 // Returns |r| - R (the event function's altitude) of the evaluated state.
 #ifndef RB_RHS_INLINE
-#define RB_RHS_INLINE 0   // 1: the evaluation is inlined at its seven sites (no call / argument moves; ~45 KB of code)
-#endif
+#define RB_RHS_INLINE 1   // 1 (default): the evaluation is inlined at its seven sites; 0: one subroutine, seven calls.
+#endif                    // Measured on B200 (profiles/r2a_*): inlined 2499 thread-instructions per trajectory-step in the dense
+                          // atmosphere against 2733 for the subroutine (12 argument moves per call, as many as the old flattened
+                          // loop spent on its `switch`); its 61 KB of code cost 0.7 no-instruction stalls per issue and it is
+                          // still 4.6 % faster (the FP64 issue slots, 2 cycles each, are 72 % of the issue port either way).
 #if RB_RHS_INLINE
 #define RB_RHS_LINKAGE __forceinline__
 #else
