@@ -84,14 +84,18 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 // Stage state of stage S from the K rows in shared memory: Ka_j, component c at Kt + (j*3 + c)*BLOCK*8 (Kt = 32-bit
-// shared address of this thread's slot-0 entry; all offsets are immediates of the LDS).
+// shared address of this thread's slot-0 entry; all offsets are immediates of the LDS).  Ka_{S-1} has just been
+// evaluated: it comes in registers (klast) -- the same value its slot holds, three loads fewer.
 template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state(uint32_t kt, const double y[6], const HTableau &ht, double ys[6]) {
+__device__ __forceinline__ void stage_state(uint32_t kt, const double y[6], const HTableau &ht, double ys[6], const double klast[3]) {
     double k[6][3];
 #pragma unroll
     for (int j = 0; j < S; ++j) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) k[j][c] = lds_f64(kt + (uint32_t)((j * K_ROWS + c) * BLOCK * 8));
+        for (int c = 0; c < 3; ++c) {
+            if (j == S - 1) k[j][c] = klast[c];
+            else k[j][c] = lds_f64(kt + (uint32_t)((j * K_ROWS + c) * BLOCK * 8));
+        }
     }
     stage_update<S>(ht, k, y, ys);
 }
@@ -223,11 +227,12 @@ __device__ __noinline__ void nan_rows_at(double *column, int64_t sample_stride, 
     nan_rows_at((p).samples + (first) * (p).sample_stride + (col), (p).sample_stride, (p).field_stride, (last) - (first) + 1)
 
 // ---------------------------------------------------------------- the hot kernel
-// Shared memory per block: [2 x tile][Ka slots: 6 x 3 x BLOCK][y_n backup: 6 x BLOCK][bc, g_old: 2 x BLOCK][2 mbarriers]
+// Shared memory per block: [2 x tile][Ka slots: 6 x 3 x BLOCK][y_n backup: 6 x BLOCK][bc, g_old: 2 x BLOCK]
+//                          [lookup-table image, TAB_DOUBLES][2 mbarriers]
 constexpr int PARK_ROWS = 8;   // per-thread doubles parked in shared memory: y_n[6], bc, g_old
 template <int BLOCK>
 constexpr size_t propagate_smem_bytes() {
-    return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + (K_SLOTS * K_ROWS + PARK_ROWS) * BLOCK) + 2 * sizeof(uint64_t);
+    return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + (K_SLOTS * K_ROWS + PARK_ROWS) * BLOCK + TAB_DOUBLES) + 2 * sizeof(uint64_t);
 }
 
 // The acceleration evaluation exists ONCE in the kernel, as a subroutine the seven evaluation sites of a step call
@@ -249,14 +254,16 @@ constexpr size_t propagate_smem_bytes() {
 #else
 #define RB_RHS_LINKAGE __noinline__
 #endif
+//   tabs  32-bit shared address of the block's lookup-table image (rb_math.cuh TabShared)
+//   a     the acceleration, also handed back in registers: the next stage's state uses it without reloading it
 template <int BLOCK, bool SKIP>
-__device__ RB_RHS_LINKAGE double rhs_eval(uint32_t ent, uint32_t park, uint32_t kdst, double x, double y, double z, double vx,
-                                        double vy, double vz) {
+__device__ RB_RHS_LINKAGE double rhs_eval(uint32_t ent, uint32_t park, uint32_t kdst, uint32_t tabs, double x, double y, double z,
+                                        double vx, double vy, double vz, double a[3]) {
     const double *e = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)ent));
     const double r[3] = {x, y, z}, v[3] = {vx, vy, vz};
     const double *bcp = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)(park + 6u * BLOCK * 8u)));
-    double a[3], alt;
-    acceleration<false, SKIP>(e, r, v, bcp, a, nullptr, &alt);
+    double alt;
+    acceleration<false, SKIP, TabShared>(e, r, v, bcp, a, nullptr, &alt, TabShared{tabs});
     sts_f64(kdst, a[0]); sts_f64(kdst + BLOCK * 8, a[1]); sts_f64(kdst + 2 * BLOCK * 8, a[2]);
     return alt;
 }
@@ -267,7 +274,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     double *tiles = reinterpret_cast<double *>(smem_raw);
     double *Ks = tiles + TILE_BUFFERS * TILE_DOUBLES;
     double *Park = Ks + K_SLOTS * K_ROWS * BLOCK;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(Park + PARK_ROWS * BLOCK);
+    double *Tab = Park + PARK_ROWS * BLOCK;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Tab + TAB_DOUBLES);
 
     const int n_live = *p.n_live;
     const int64_t i0 = (int64_t)blockIdx.x * BLOCK;
@@ -326,55 +334,62 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     const uint32_t Pk = Kt + K_SLOTS * K_ROWS * BLOCK * 8;   // parked: y_n[c] at Pk + c*BLOCK*8, bc at row 6, g_old at row 7
     sts_f64(Pk + 6 * BLOCK * 8, make_body(b_cd, b_area, b_mass).bc);
     sts_f64(Pk + 7 * BLOCK * 8, event_g(y, p.event_altitude));
-    __syncthreads();  // barrier init visible to all before anyone waits
+    // the block's copy of the lookup tables (2^(j/32), atan reference angles, atmosphere layer records)
+    for (int j = threadIdx.x; j < TAB_DOUBLES; j += BLOCK)
+        Tab[j] = j < TAB_ATAN ? g_exp_tab[j] : (j < TAB_LAYER ? (&g_atan_tab[0][0])[j - TAB_ATAN] : (&g_layer[0][0])[j - TAB_LAYER]);
+    uint32_t Tb = smem_u32(Tab);
+    asm volatile("" : "+r"(Tb));
+    __syncthreads();  // barrier init and table image visible to all
 
     int to_sample = (int)(p.k_first * p.out_stride - p.run_step0);  // steps until the next stored sample
     int64_t next_k = p.k_first;
+    double ka[3] = {0.0, 0.0, 0.0};   // the acceleration evaluated last (in registers as well as in its K slot)
+    // (A ROTATED form of this loop -- each iteration opening with the FSAL evaluation, which removes the separate first
+    //  evaluation and one of the seven inlined copies of the acceleration code, 51 KB instead of 57 -- measured 0.5 %
+    //  SLOWER (10.53 vs 10.58 G trajectory-steps/s): with the lookup tables in shared memory the instruction cache no
+    //  longer limits, and the rotation adds a per-step test.  It also ran into a ptxas 12.9 defect worth knowing: a loop
+    //  variable whose INITIAL value is the address of the dynamic shared memory itself is taken for "the shared-memory
+    //  base" and other shared addresses are rematerialised from its register inside the loop, after it has moved on.
+    //  Below, `ent` is derived per tile and never equals that constant symbolically.)
     int t = 0;
     for (; t < n_tiles; ++t) {
         mbar_wait(&bars[t % TILE_BUFFERS], (uint32_t)((t / TILE_BUFFERS) & 1));
         uint32_t ent = smem_u32(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES);   // entry 5 m of the tile = t_n of its step m
         const int ts = tile_steps_of(t);
         // the launch's very first evaluation: Ka_0 = a(t_n, y_n) (later steps inherit it from the previous step: FSAL)
-        if (t == 0 && alive) rhs_eval<BLOCK, SKIP>(ent, Pk, Kt, y[0], y[1], y[2], y[3], y[4], y[5]);
+        if (t == 0 && alive) rhs_eval<BLOCK, SKIP>(ent, Pk, Kt, Tb, y[0], y[1], y[2], y[3], y[4], y[5], ka);
         for (int m = 0; m < ts; ++m) {
             if (alive) {
                 constexpr uint32_t EB = HOT_DOUBLES * 8, SB = K_ROWS * BLOCK * 8;   // bytes per table entry / per K slot
                 double ys[6];
-                stage_state<1, BLOCK>(Kt, y, p.ht, ys);
-                rhs_eval<BLOCK, SKIP>(ent + 1 * EB, Pk, Kt + 1 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
-                stage_state<2, BLOCK>(Kt, y, p.ht, ys);
-                rhs_eval<BLOCK, SKIP>(ent + 2 * EB, Pk, Kt + 2 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
-                stage_state<3, BLOCK>(Kt, y, p.ht, ys);
-                rhs_eval<BLOCK, SKIP>(ent + 3 * EB, Pk, Kt + 3 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
-                stage_state<4, BLOCK>(Kt, y, p.ht, ys);
-                rhs_eval<BLOCK, SKIP>(ent + 4 * EB, Pk, Kt + 4 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
-                stage_state<5, BLOCK>(Kt, y, p.ht, ys);
-                rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt + 5 * SB, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5]);
-                // the step's end point (stage 6; row 6 of A = B).  y_n is parked in shared memory, y becomes y_{n+1},
-                // and its evaluation (at t_{n+1}, the entry of stage 5) is the next step's Ka_0 (slot 0: every Ka of this
-                // step has been consumed by then).  The event function is the altitude that evaluation returns.
+                stage_state<1, BLOCK>(Kt, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 1 * EB, Pk, Kt + 1 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<2, BLOCK>(Kt, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 2 * EB, Pk, Kt + 2 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<3, BLOCK>(Kt, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 3 * EB, Pk, Kt + 3 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<4, BLOCK>(Kt, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 4 * EB, Pk, Kt + 4 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<5, BLOCK>(Kt, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt + 5 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
 #pragma unroll
                 for (int c = 0; c < 6; ++c) sts_f64(Pk + c * BLOCK * 8, y[c]);
-                stage_state<6, BLOCK>(Kt, y, p.ht, ys);
+                stage_state<6, BLOCK>(Kt, y, p.ht, ys, ka);
 #pragma unroll
                 for (int c = 0; c < 6; ++c) y[c] = ys[c];
-                const double alt_new = rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt, y[0], y[1], y[2], y[3], y[4], y[5]);
+                const double alt_new = rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt, Tb, y[0], y[1], y[2], y[3], y[4], y[5], ka);
                 const double g_new = alt_new - p.event_altitude;
                 const double g_old = lds_f64(Pk + 7 * BLOCK * 8);
                 const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
-                // non-finite detection on the exponent bits of |r| - R (|r|^2 = inf or NaN makes it NaN; a
-                // NaN/Inf velocity reaches r one step later; the FP64 pipe is the bottleneck, integer compares are free)
                 const bool finite = (__double2hiint(alt_new) & 0x7ff00000) != 0x7ff00000;
-                const bool hit = g_old >= 0.0 && g_new <= 0.0;   // scipy ivp.py:151, direction -1
+                const bool hit = g_old >= 0.0 && g_new <= 0.0;
                 if (!finite || hit) {
                     alive = false;
                     p.status[tid] = finite ? RB_TRAJ_IMPACTED : RB_TRAJ_NONFINITE;
                     if (p.impact_step) p.impact_step[tid] = (int32_t)step_abs;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) y[c] = lds_f64(Pk + c * BLOCK * 8);   // y_n: where k_refine restarts the step
+                    for (int c = 0; c < 6; ++c) y[c] = lds_f64(Pk + c * BLOCK * 8);
                     if (p.packed && p.samples) {
-                        // (k_refine stores the sample of a grid time that coincides with the event time: where)
                         if (finite && to_sample == 1) {
                             p.edge_slot[2 * (int64_t)tid] = p.slab_offset + (next_k - p.sample_row0) * p.sample_stride + RB_SAMPLE_COL();
                             p.edge_slot[2 * (int64_t)tid + 1] = p.field_stride;
@@ -395,11 +410,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
             }
             ent += RB_STAGES_PER_STEP * HOT_DOUBLES * 8;
             if (--to_sample == 0) { to_sample = (int)p.out_stride; ++next_k; }
-            // warp-ballot retirement: a warp with no live lane leaves (warp 0 stays while tiles remain to be issued)
             if (!__any_sync(0xffffffffu, alive) && (threadIdx.x >= 32 || t + TILE_BUFFERS >= n_tiles)) goto done;
         }
         if (t + TILE_BUFFERS < n_tiles) {
-            __syncthreads();  // everyone is done reading this tile's buffer
+            __syncthreads();
             if (threadIdx.x == 0) issue_tile(t + TILE_BUFFERS);
         }
     }

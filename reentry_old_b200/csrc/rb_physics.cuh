@@ -97,9 +97,17 @@ static_assert(rb_hi_word_(90000.0) == 0x40F5F900 && rb_hi_word_(1.0) == 0x3FF000
 
 #if defined(__CUDACC__)
 __constant__ Consts c_k = RB_CONSTS_INIT;
-// per-layer records read with a LANE-dependent index: through L1 (LDG.128) instead of the constant bank, whose
-// indexed loads replay once per distinct address in the warp
+// per-layer records read with a LANE-dependent index: through L1 (LDG.128) or the block's shared-memory table image
+// (table policy of rb_math.cuh) instead of the constant bank, whose indexed loads replay once per distinct address
 __device__ const double __align__(64) g_layer[RB_N_LAYERS][8] = RB_L8_(RB_LAYER_);
+__device__ __forceinline__ void tab_layer(const TabGlobal &, int i, double lay[6]) {
+    const double2 l01 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][0]));
+    const double2 l23 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][2]));
+    const double2 l45 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][4]));
+    lay[0] = l01.x; lay[1] = l01.y; lay[2] = l23.x; lay[3] = l23.y; lay[4] = l45.x; lay[5] = l45.y;
+}
+__device__ __forceinline__ void tab_layer(const TabShared &tb, int i, double lay[6]) { tb.layer(i, lay); }
+static_assert(RB_N_LAYERS == 8, "table image layout (rb_math.cuh TAB_LAYER) assumes 8 layer records");
 #endif
 static const Consts h_k = RB_CONSTS_INIT;
 #if defined(__CUDA_ARCH__)
@@ -112,13 +120,13 @@ struct Body {  // per-trajectory constant bc = 0.5 Cd A / m (SpacecraftModel.Cd 
     double bc;
 };
 struct RhsOut;
-template <bool DIAG, bool SKIP = false>
+template <bool DIAG, bool SKIP = false, class TB = TabGlobal>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const double *bcp,
-                        double a[3], RhsOut *diag, double *altitude_out = nullptr);
+                        double a[3], RhsOut *diag, double *altitude_out = nullptr, const TB &tb = TB());
 template <bool DIAG, bool SKIP = false>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
                         double a[3], RhsOut *diag, double *altitude_out = nullptr) {
-    acceleration<DIAG, SKIP>(e, r, v, &b.bc, a, diag, altitude_out);
+    acceleration<DIAG, SKIP, TabGlobal>(e, r, v, &b.bc, a, diag, altitude_out, TabGlobal());
 }
 RB_HD Body make_body(double cd, double area, double mass) { return Body{0.5 * cd * area / mass}; }
 
@@ -166,26 +174,30 @@ RB_HD void spacecraft_temperature(double v_norm, double atmo_T, double a_drag_no
 // iteration and ONE inverse-trig call (the returned angle) instead of 2 + n atan2 and 1 + n
 // sincos.  Only |lat| is needed by the density (spacecraft_model.py:76).
 //   p2 = x^2 + y^2, inv_p = 1/sqrt(p2) are passed in (shared with the caller).
+// FAST (the hot RHS, which needs |lat| to 1e-11 rad at most): second-order rsqrt (rb_math.cuh); the same iterates to
+// 1e-12 and the same break decisions except within 1e-12 of the tolerance.
+template <bool FAST = false>
 RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, double &B_out) {
     const double p = p2 * inv_p;
     // theta = atan2(z R, p (1 - e2 R)) -> (sin, cos) by normalisation
     // (scale invariant: (z R, p (1 - e2 R)) is normalised as (z, p (1 - e2 R) / R) -- one multiply and one constant less)
     const double tb = p * KC(one_m_e2r_over_r);
-    const double th = rb_rsqrt(fma(z, z, tb * tb));
+    const double th = FAST ? rb_rsqrt_q(fma(z, z, tb * tb)) : rb_rsqrt(fma(z, z, tb * tb));
     const double st = z * th, ct = tb * th;
     // lat_0 = atan2(z + e2R sin^3 theta, p - e2R cos^3 theta)
     double A = fma(KC(e2r), st * (st * st), z), B = fma(-KC(e2r), ct * (ct * ct), p);
     const double zp = z * inv_p;          // A of every later iterate
     const double ke = KC(e2r) * inv_p;    // e2 R / p
     {
-        const double q = rb_rsqrt(fma(B, B, KC(one_m_e2) * (A * A)));
+        const double qa = fma(B, B, KC(one_m_e2) * (A * A));
+        const double q = FAST ? rb_rsqrt_q(qa) : rb_rsqrt(qa);
         const double Bn = fma(-ke * B, q, 1.0);
         const bool conv = fabs(fma(A, Bn, -(zp * B))) < KC(tan_tol) * fma(B, Bn, A * zp);
         if (!conv) {
             A = zp; B = Bn;
             const double zp2 = zp * zp, g = KC(one_m_e2) * zp2, azp = fabs(zp);
             for (int it = 1; it < RB_GEODETIC_MAX_ITER; ++it) {
-                const double q2 = rb_rsqrt(fma(B, B, g));
+                const double q2 = FAST ? rb_rsqrt_q(fma(B, B, g)) : rb_rsqrt(fma(B, B, g));
                 const double Bn2 = fma(-ke * B, q2, 1.0);
                 const double d = azp * fabs(Bn2 - B), S = fma(B, Bn2, zp2);
                 if (d < KC(tan_tol) * S) break;
@@ -194,20 +206,24 @@ RB_HD void geodetic_pair(double p2, double inv_p, double z, double &A_out, doubl
                 // <= 1.03 e2 R/|r| < 0.008 (|r| > 0.9 R, 0.99 < B < 1), and the right-hand side of the test
                 // shrinks by at most 0.98: d < 122 tol S (100 is used) here PROVES the next pass would break and return
                 // this Bn2 -- the pass that only confirms convergence is not computed (same returned iterate).
+                // (Peeling the first pass out of the loop was tried: the copy of the loop it leaves behind in each of
+                // the step kernel's seven inlined evaluations costs more instruction cache than the peel saves issue slots,
+                // and an out-of-line copy makes the callers spill.)
                 if (d < 0x1.a36e3p-14 * S) break;   // 1.0e-4 = 100 tan(1e-6), written with a zero low word (immediate)
             }
         }
     }
     A_out = A; B_out = B;
 }
-RB_HD double pair_abs_latitude_rad(double A, double B) {
+template <bool FAST = false, class TB = TabGlobal>
+RB_HD double pair_abs_latitude_rad(double A, double B, const TB &tb = TB()) {
     const double nr = rb_rsqrt_seed(fma(A, A, B * B));   // approximate length: atan2 is scale free
-    return rb_atan2_unit(fabs(A) * nr, B * nr);
+    return rb_atan2_unit<FAST>(fabs(A) * nr, B * nr, tb);
 }
-RB_HD double pair_abs_latitude_deg(double A, double B) { return pair_abs_latitude_rad(A, B) * KC(rad2deg); }
+RB_HD double pair_abs_latitude_deg(double A, double B) { return pair_abs_latitude_rad<false>(A, B) * KC(rad2deg); }
 RB_HD double geodetic_abs_latitude_deg(double p2, double inv_p, double z) {
     double A, B;
-    geodetic_pair(p2, inv_p, z, A, B);
+    geodetic_pair<false>(p2, inv_p, z, A, B);
     return pair_abs_latitude_deg(A, B);
 }
 
@@ -217,7 +233,7 @@ RB_HD void geodetic_full(double x, double y, double z, double &lat_deg, double &
     const double p2 = fma(x, x, y * y);
     const double ip = rb_rsqrt(p2);
     double A, B;
-    geodetic_pair(p2, ip, z, A, B);
+    geodetic_pair<false>(p2, ip, z, A, B);
     const double n2 = fma(A, A, B * B);
     const double nr = rb_rsqrt(n2);
     const double a = rb_atan2_unit(fabs(A) * nr, B * nr) * KC(rad2deg);
@@ -241,10 +257,21 @@ RB_HD double haversine(double lat1, double lon1, double lat2, double lon2) {
 // (spacecraft_model.py:181-188, :71-99, :148-168, :110-127).  solar_time = time-only part of the
 // solar factor from the time table.  The two exponentials of the top layer (:84 and :89) are
 // one exp of the summed exponent.
-RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out) {
+template <class TB = TabGlobal>
+RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out, const TB &tb = TB()) {
     // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
     // solar_m1 = solar_time - 1 (both from the time table)
-    if (altitude <= 0.0) { T_out = RB_SEA_LEVEL_T; return RB_SEA_LEVEL_RHO; }
+    if (altitude <= 0.0) {   // (below the ellipsoid's equatorial radius: never on a live trajectory's hot path, so the
+#if defined(__CUDA_ARCH__)   //  constant is formed HERE -- a volatile asm cannot be hoisted above the branch)
+        double sea;
+        asm volatile("mov.f64 %0, 0d3FF399999999999A;" : "=d"(sea));   // RB_SEA_LEVEL_RHO = 1.225
+        T_out = RB_SEA_LEVEL_T;
+        return sea;
+#else
+        T_out = RB_SEA_LEVEL_T;
+        return RB_SEA_LEVEL_RHO;
+#endif
+    }
     double factor = solar_time;
     // From here on altitude > 0 (or NaN): the thresholds (90 km, the layer breakpoints) have zero low words, so
     // `altitude >= b` is the integer compare of the high words -- one issue cycle instead of a DSETP's two.
@@ -256,11 +283,7 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
 #else
 #define RB_ALT_GE(b) (altitude >= (b))
 #endif
-    if (!RB_ALT_GE(RB_SOLAR_BLEND_ALT)) {
-        // (the exponent lies in [-2.6, 0.8] for 0 < altitude < 90 km: no clamp)
-        const double normalized = rb_rcp(1.0 + rb_exp_bounded(fma(-KC(sig_ks), altitude, KC(sig_c))));   // 1 / (1 + e^(-k (x - x0)))
-        factor = fma(solar_m1, normalized, 1.0);
-    }
+    const bool blend = !RB_ALT_GE(RB_SOLAR_BLEND_ALT);   // below 90 km: sigmoid blend of the solar factor, :163-166
     // rho = c0 e^arg (latitude_factor factor): every layer funnels into ONE exp, so that a warp whose lanes sit in
     // different layers (isothermal / gradient / top) does not execute one exponential per layer kind
     double arg, c0, T;
@@ -280,10 +303,8 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         i += (altitude >= KC(bp[i + 1])) ? 1 : 0;
 #endif
 #if defined(__CUDA_ARCH__)
-        const double2 l01 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][0]));
-        const double2 l23 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][2]));
-        const double2 l45 = __ldg(reinterpret_cast<const double2 *>(&g_layer[i][4]));
-        const double lay[6] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
+        double lay[6];
+        tab_layer(tb, i, lay);
 #else
         const double *__restrict__ lay = KC(layer[i]);
 #endif
@@ -296,14 +317,19 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         c0 = lay[5] * rb_rcp(T);                                        // P / (R_GAS T), :88
     }
     T_out = T;
-    return (c0 * rb_exp_bounded(arg)) * (latitude_factor * factor);
+    if (blend)   // (the sigmoid's exponent lies in [-2.6, 0.8] for 0 < altitude < 90 km: no clamp)
+        factor = fma(solar_m1, rb_rcp(1.0 + rb_exp_bounded(fma(-KC(sig_ks), altitude, KC(sig_c)), tb)), 1.0);   // 1 + (f - 1) / (1 + e^(-k (x - x0)))
+    // (evaluating the two exponentials interleaved, to load their coefficients once, measured no gain: 10.14 vs 10.15 G)
+    const double ex = rb_exp_bounded(arg, tb);
+    return (c0 * ex) * (latitude_factor * factor);
 #undef RB_ALT_GE
 }
 // bcp: where the body constant bc = Cd A / (2 m) is read from AT ITS USE (the very end of the evaluation): the step
 // kernel parks it in shared memory instead of holding two registers through the whole evaluation.
-template <bool DIAG, bool SKIP>
+template <bool DIAG, bool SKIP, class TB>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const double *bcp,
-                        double a[3], RhsOut *diag, double *altitude_out) {
+                        double a[3], RhsOut *diag, double *altitude_out, const TB &tb) {
+    constexpr bool FAST = !DIAG;   // second-order rsqrt / rcp where only the latitude factor or a third-body term is fed
     const double x = r[0], y = r[1], z = r[2];
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
@@ -354,13 +380,13 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         } else {   // the indirect terms are already in (ax, ay, az): accumulate the direct ones
             {
                 const double dx = e[H_MOON + 0] - x, dy = e[H_MOON + 1] - y, dz = e[H_MOON + 2] - z;
-                const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double id = rb_rsqrt_q(fma(dz, dz, fma(dx, dx, dy * dy)));
                 const double k3 = KC(moon_k) * (id * id * id);
                 ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
             }
             {
                 const double dx = e[H_SUN + 0] - x, dy = e[H_SUN + 1] - y, dz = e[H_SUN + 2] - z;
-                const double id = rb_rsqrt(fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double id = rb_rsqrt_q(fma(dz, dz, fma(dx, dx, dy * dy)));
                 const double k3 = KC(sun_k) * (id * id * id);
                 ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
             }
@@ -372,16 +398,16 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     if (altitude_out) *altitude_out = altitude;          // (the step kernel's event function reuses it)
     if (!SKIP || altitude <= RB_NEGLIGIBLE_DRAG_ALTITUDE_) {
         // the ECEF rotation is about z: p = sqrt(xe^2 + ye^2) = sqrt(x^2 + y^2), ze = z
-        const double ip = rb_rsqrt(p2);
+        const double ip = FAST ? rb_rsqrt_q(p2) : rb_rsqrt(p2);
         double gA, gB;
-        geodetic_pair(p2, ip, z, gA, gB);
+        geodetic_pair<FAST>(p2, ip, z, gA, gB);
         third_bodies();
         double T, rho, lat_deg = 0.0;
         if (DIAG) {
             lat_deg = pair_abs_latitude_deg(gA, gB);
-            rho = density(altitude, fma(KC(latc), lat_deg, 1.0), e[E_SOLAR], e[E_SOLAR] - 1.0, T);
+            rho = density(altitude, fma(KC(latc), lat_deg, 1.0), e[E_SOLAR], e[E_SOLAR] - 1.0, T, tb);
         } else {   // radians straight into the latitude factor (the degree conversion folds into the coefficient)
-            rho = density(altitude, fma(KC(latc_rad), pair_abs_latitude_rad(gA, gB), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T);
+            rho = density(altitude, fma(KC(latc_rad), pair_abs_latitude_rad<true>(gA, gB, tb), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T, tb);
         }
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
         const double vn = w2 * rb_rsqrt(w2);

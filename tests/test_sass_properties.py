@@ -53,13 +53,29 @@ def test_step_kernel_register_and_instruction_budget(sass):
     ops = _ops(body)
     fp64 = sum(ops.get(k, 0) for k in ("DFMA", "DMUL", "DADD", "DSETP"))
     total = sum(ops.values())
-    assert fp64 <= 420 and total <= 1450, (fp64, total)  # 406 / 1400 at the end of round 1 (7 x that in the first kernel)
-    assert ops.get("LDL", 0) <= 1 and ops.get("STL", 0) <= 2   # one 8-byte value lives on the stack (reloaded once per RHS)
+    # seven inlined evaluations (the step's six + the launch's first): ~3.7 k instructions, 45 % of them FP64
+    # (the flattened-loop kernel of round 1: 1.4 k instructions, 29 % FP64 -- and 10 % more executed per step)
+    assert total <= 3900 and fp64 >= 0.44 * total, (fp64, total)
+    assert ops.get("LDL", 0) == 0 and ops.get("STL", 0) == 0   # nothing lives on the stack
+    assert ops.get("CALL", 0) <= 12                            # only cold paths (64-bit division, NaN rows of a retiring lane) are calls
+
+
+def test_flop_calibration_matches_the_built_kernel(sass):
+    """bench.py's roofline multiplies trajectory-steps by profiles/flop_per_traj_step.json, an ncu measurement of ONE
+    build of the kernel.  The file records that build's static FP64 instruction mix; if the kernel in the tree has a
+    different mix the calibration is stale and this test says so (re-run tools/gpu_ncu_pass.sh, tools/calibrate_flop.py)."""
+    _, body = sass
+    ops = _ops(body)
+    cal = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "flop_per_traj_step.json")))
+    want = cal["static_fp64_of_calibrated_kernel"]
+    have = {k: ops.get(k, 0) for k in ("DFMA", "DMUL", "DADD")}
+    assert have == want, (have, want)
 
 
 def test_step_kernel_shared_memory_accesses_have_immediate_offsets(sass):
     _, body = sass
     lds = re.findall(r"LDS(?:\.\d+)?\s+R\d+, \[(R\d+)(\+0x[0-9a-f]+)?\]", body)
-    assert len(lds) >= 60                                 # 63 K-row loads per step + the table entries
+    assert len(lds) >= 100                                # per evaluation: K rows, time-table entry, parked values, lookup tables
     with_imm = sum(1 for _, off in lds if off)
     assert with_imm >= 0.8 * len(lds)                     # one base register, offsets folded into the instruction
+    assert body.count("LDG.E.64.CONSTANT") <= 4   # (only the copy of the lookup tables into shared memory at kernel start reads them from global memory)
