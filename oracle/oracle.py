@@ -29,14 +29,30 @@ class RhsParts(C.Structure):
     ]
 
 
+FMA_LIB_PATH = os.path.join(HERE, "libreentry_oracle_fma.so")
+_lib_fma = None
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "reentry_oracle.c")
     hdr = os.path.join(os.path.dirname(HERE), "include", "reentry_constants.h")
-    stale = (not os.path.exists(LIB_PATH)) or any(
-        os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in (src, hdr))
-    if force or stale:
-        subprocess.run(["make", "-C", HERE, "-B", "libreentry_oracle.so"], check=True, capture_output=True)
+    for path in (LIB_PATH, FMA_LIB_PATH):
+        stale = (not os.path.exists(path)) or any(os.path.getmtime(p) > os.path.getmtime(path) for p in (src, hdr))
+        if force or stale:
+            subprocess.run(["make", "-C", HERE, "-B", os.path.basename(path)], check=True, capture_output=True)
     return LIB_PATH
+
+
+def lib_fma():
+    """The same C source compiled with FMA contraction: an equally valid second rounding of the algorithm (see Makefile).
+    Only rbo_propagate is used from it."""
+    global _lib_fma
+    if _lib_fma is None:
+        if not os.path.exists(FMA_LIB_PATH):
+            build()
+        _lib_fma = C.CDLL(FMA_LIB_PATH)
+        _lib_fma.rbo_propagate.restype = C.c_int
+    return _lib_fma
 
 
 def lib():
@@ -168,8 +184,8 @@ def max_threads() -> int:
     return lib().rbo_max_threads()
 
 
-def propagate(y0, Cd, A, m, epoch_jd, gmst0, t0, dt, n_steps, stride=1, want_samples=True, n_threads=0):
-    """Fixed-step DP5 ensemble on the CPU.  y0 [N,6].  Returns dict:
+def propagate(y0, Cd, A, m, epoch_jd, gmst0, t0, dt, n_steps, stride=1, want_samples=True, n_threads=0, fma=False):
+    """Fixed-step DP5 ensemble on the CPU.  y0 [N,6].  fma=True: the FMA-contracted build (second rounding).  Returns dict:
     samples [N, n_out, 8] (x,y,z,vx,vy,vz,altitude,speed; NaN after the event) or None,
     impact_step [N] i32 (-1 none), impact_time [N], final_state [N,6], status [N] u8,
     n_samples [N] i64, threads (int)."""
@@ -185,7 +201,7 @@ def propagate(y0, Cd, A, m, epoch_jd, gmst0, t0, dt, n_steps, stride=1, want_sam
     status = np.empty(N, dtype=np.uint8)
     n_samples = np.empty(N, dtype=np.int64)
     P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-    used = lib().rbo_propagate(
+    used = (lib_fma() if fma else lib()).rbo_propagate(
         C.c_int64(N), P(y0), P(Cd), P(A), P(m), C.c_double(epoch_jd), C.c_double(gmst0), C.c_double(t0),
         C.c_double(dt), C.c_int64(n_steps), C.c_int64(stride), P(samples), P(impact_step), P(impact_time),
         P(final_state), P(status), P(n_samples), C.c_int(n_threads))

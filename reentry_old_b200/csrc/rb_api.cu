@@ -32,6 +32,16 @@ using namespace rb;
 #ifndef RB_MIN_BLOCKS
 #define RB_MIN_BLOCKS 6
 #endif
+// (Narrower blocks for ensembles that do not fill one wave of the machine -- 32- and 64-thread blocks with 4-step tiles,
+//  which spread the warps to within one or two per SM -- were built and measured on the two sub-wave configurations of
+//  BASELINE.json: C3 (100 k trajectories) 9.42 G trajectory-steps/s against 10.1 G with 128-thread blocks, C4 (50 k)
+//  9.46 against 9.53 (profiles/r2e_configs_c3_c4.jsonl).  One shape it is.)
+template <bool SKIP>
+static void launch_step(const StepParams &sp, int64_t live_bound, cudaStream_t s) {
+    const unsigned grid = (unsigned)((live_bound + RB_BLOCK - 1) / RB_BLOCK);
+    k_propagate<RB_BLOCK, RB_MIN_BLOCKS, SKIP><<<grid, RB_BLOCK, propagate_smem_bytes<RB_BLOCK>(), s>>>(sp);
+}
+
 struct rb_ctx {
     int device = 0;
     char err[512] = {0};
@@ -459,7 +469,6 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
 
     int64_t done = 0;
     int64_t launch_idx = 0;
-    const size_t smem = propagate_smem_bytes<RB_BLOCK>();
     while (done < run->n_steps) {
         if (early && launch_idx >= 2) {  // look at the live counts published 2 launches ago (never blocks the GPU)
             const int slot = (int)((launch_idx - 2) & 7);
@@ -491,7 +500,6 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             if (pt.finished) continue;
             sp.live = ctx->d_live[pt.cur] + pt.start;
             sp.n_live = pt.n_live;
-            const unsigned grid = (unsigned)((pt.live_bound + RB_BLOCK - 1) / RB_BLOCK);
             // sample rows this launch writes: k with k * out_stride in (run_step0, run_step0 + steps]
             const int64_t k_first = sp.run_step0 / run->out_stride + 1, k_last = (sp.run_step0 + steps) / run->out_stride;
             // (once back-pressure has been seen the link is the bottleneck of this call: from then on only rows without
@@ -529,8 +537,8 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
                 k_fill_nan_2d<<<(unsigned)((pt.count * hgt + 255) / 256), 256, 0, pt.s>>>(route->staging + slice, pt.count, hgt, n);
                 sp.samples = route->staging;
             }
-            if (skip_drag) k_propagate<RB_BLOCK, RB_MIN_BLOCKS, true><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
-            else k_propagate<RB_BLOCK, RB_MIN_BLOCKS, false><<<grid, RB_BLOCK, smem, pt.s>>>(sp);
+            if (skip_drag) launch_step<true>(sp, pt.live_bound, pt.s);
+            else launch_step<false>(sp, pt.live_bound, pt.s);
             CK(cudaGetLastError());
             if (slab) {
                 if (hook) hook->after_slab(n_slabs, out->slabs[n_slabs], pt.s);

@@ -81,11 +81,11 @@ def main():
     if "c2" in which:
         run(CF.c2_reentry_mc(int(1_000_000 * scale)), 64, 2048)
     if "c3" in which:
-        run(CF.c3_sso_decay(int(100_000 * scale)), 16, 8640, drift_n=2)
-        run(CF.c3_sso_decay(int(100_000 * scale)), 16, 8640, drift_n=2, skip=True)
+        run(CF.c3_sso_decay(int(100_000 * scale)), 16, 8640, drift_n=16)
+        run(CF.c3_sso_decay(int(100_000 * scale)), 16, 8640, skip=True)
     if "c4" in which:
-        run(CF.c4_geo_heo(int(50_000 * scale)), 16, 8640, drift_n=2)
-        run(CF.c4_geo_heo(int(50_000 * scale)), 16, 8640, drift_n=2, skip=True)
+        run(CF.c4_geo_heo(int(50_000 * scale)), 16, 8640, drift_n=16)
+        run(CF.c4_geo_heo(int(50_000 * scale)), 16, 8640, skip=True)
 
 
 if __name__ == "__main__":
