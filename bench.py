@@ -599,7 +599,7 @@ def main():
         barrier()
         el = time.perf_counter() - t0
         e2e_steps = steps_of(rh.impact_step.numpy(), w.n_steps)
-        sent = int(rh.packed.used) * 8
+        sent = int(rh.stats["sample_bytes_sent"])        # what the copy engine moved: live columns of every slab
         tt = torch.tensor([el, float(e2e_steps), float(sent)], dtype=torch.float64, device=dev)
         if world > 1:
             a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)

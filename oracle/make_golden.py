@@ -22,6 +22,7 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
   thermal.npz          N1: thermal entries of the unmodified equations_of_motion dict + direct
                        spacecraft_temperature calls
   adaptive.npz         N4: run_simulation as shipped (scipy adaptive RK45) on four launch geometries
+  adaptive_rk23.npz    the same with sim_type='RK23' (scipy's Bogacki-Shampine 3(2) pair)
   recorded_trajectory.json   first samples of the trajectory embedded in temperature_model.py:104-105
 
     python oracle/make_golden.py        # ~2-3 min (numba JIT of the reference leaves dominates)
@@ -314,9 +315,10 @@ def thermal(sm, const):
     return out
 
 
-def adaptive(sm, const):
+def adaptive(sm, const, sim_type="RK45"):
     """N4: SpacecraftModel.run_simulation AS SHIPPED (scipy adaptive RK45, rtol 1e-8, atol 1e-10, spacecraft_model.py:516)
-    on four launch geometries; plus the accepted-step times of the same solve_ivp call without t_eval."""
+    on four launch geometries; plus the accepted-step times of the same solve_ivp call without t_eval.
+    sim_type='RK23': the same through the constructor's sim_type (app.py:51 offers it; spacecraft_model.py:516 passes it on)."""
     from scipy.integrate import solve_ivp
 
     cases = [  # (Cd, A, m, gmst0, (v, lat, lon, alt, az, gamma), tf, dt_out)
@@ -327,7 +329,7 @@ def adaptive(sm, const):
     ]
     out = {"n_cases": len(cases)}
     for k, (Cd, A, m, gmst0, geo, tf, dt) in enumerate(cases):
-        mdl = sm.SpacecraftModel(Cd=Cd, A=A, m=m, epoch=R.Epoch(EPOCH_JD), gmst0=gmst0, dt=10, iter_fact=2)
+        mdl = sm.SpacecraftModel(Cd=Cd, A=A, m=m, epoch=R.Epoch(EPOCH_JD), gmst0=gmst0, sim_type=sim_type, dt=10, iter_fact=2)
         y0 = mdl.get_initial_state(*geo, gmst=gmst0)
         t_eval = np.arange(0, tf, dt)
         sol = mdl.run_simulation((0, tf), y0, t_eval)
@@ -340,7 +342,7 @@ def adaptive(sm, const):
             return sm.euclidean_norm(y[0:3]) - const.EARTH_R - 1000.0
         ev.terminal = True
         ev.direction = -1
-        s2 = solve_ivp(rhs, (0, tf), y0, method="RK45", rtol=1e-8, atol=1e-10, events=[ev])
+        s2 = solve_ivp(rhs, (0, tf), y0, method=sim_type, rtol=1e-8, atol=1e-10, events=[ev])
         te = sol.t_events[0]
         out.update({f"cfg_{k}": np.array([Cd, A, m, gmst0, tf, dt]), f"y0_{k}": y0, f"t_{k}": sol.t, f"y_{k}": sol.y,
                     f"t_event_{k}": (te[0] if len(te) else np.nan),
@@ -348,6 +350,7 @@ def adaptive(sm, const):
                     f"nfev_{k}": sol.nfev, f"status_{k}": sol.status, f"steps_t_{k}": s2.t,
                     f"altitude_{k}": sol.additional_data["altitude"]})
     out["epoch_jd"] = EPOCH_JD
+    out["sim_type"] = sim_type
     return out
 
 
@@ -370,6 +373,9 @@ def main():
     sm, cc, const = R.load()
     if "--only-adaptive" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "adaptive.npz"), **adaptive(sm, const))
+        return
+    if "--only-rk23" in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "adaptive_rk23.npz"), **adaptive(sm, const, "RK23"))
         return
     if "--only-thermal" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
@@ -402,6 +408,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "ground_track.npz"), **ground_track(cc, const))
     np.savez_compressed(os.path.join(GOLD, "thermal.npz"), **thermal(sm, const))
     np.savez_compressed(os.path.join(GOLD, "adaptive.npz"), **adaptive(sm, const))
+    np.savez_compressed(os.path.join(GOLD, "adaptive_rk23.npz"), **adaptive(sm, const, "RK23"))
     with open(os.path.join(GOLD, "recorded_trajectory.json"), "w") as f:
         json.dump(recorded_trajectory(), f)
     print("wrote", sorted(os.listdir(GOLD)))

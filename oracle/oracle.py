@@ -250,7 +250,7 @@ def spacecraft_temperature(v_norm, atmo_T, a_drag_norm, capsule_length, dt, ther
 
 
 def propagate_adaptive(y0, Cd, A, m, epoch_jd, gmst0, t_span, t_eval0, t_eval_dt, n_eval, rtol=1e-8, atol=1e-10,
-                       max_steps=100000):
+                       max_steps=100000, method="RK45"):
     """The reference's run_simulation as shipped (scipy adaptive RK45, spacecraft_model.py:516) for ONE trajectory.
     Returns dict: t [n], y [6,n], altitude [n], speed [n], t_event (NaN if none), y_final [6], status, n_accepted,
     n_rejected, nfev, step_t (accepted step end times)."""
@@ -259,7 +259,8 @@ def propagate_adaptive(y0, Cd, A, m, epoch_jd, gmst0, t_span, t_eval0, t_eval_dt
     ns = C.c_int64(); te = C.c_double(); ye = (C.c_double * 6)(); na = C.c_int64(); nr = C.c_int64(); nf = C.c_int64()
     step_t = np.full(max_steps + 1, np.nan)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
-    st = lib().rbo_propagate_adaptive(P(y0), C.c_double(Cd), C.c_double(A), C.c_double(m), C.c_double(epoch_jd),
+    lib().rbo_propagate_adaptive_method.restype = C.c_int
+    st = lib().rbo_propagate_adaptive_method(C.c_int({"RK45": 0, "RK23": 1}[method]), P(y0), C.c_double(Cd), C.c_double(A), C.c_double(m), C.c_double(epoch_jd),
                                       C.c_double(gmst0), C.c_double(t_span[0]), C.c_double(t_span[1]), C.c_double(rtol),
                                       C.c_double(atol), C.c_double(t_eval0), C.c_double(t_eval_dt), C.c_int64(n_eval), P(samples),
                                       C.byref(ns), C.byref(te), ye, C.byref(na), C.byref(nr), C.byref(nf), P(step_t),

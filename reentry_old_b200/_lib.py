@@ -22,6 +22,7 @@ RB_FLAG_DIRECT_SAMPLES = 128
 RB_FLAG_RESUME = 256
 RB_FLAG_PACKED_SAMPLES = 512
 RB_ABI_VERSION = 2
+RB_METHOD_RK45, RB_METHOD_RK23 = 0, 1
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
 RB_DIAG_FIELDS = 23
@@ -64,7 +65,8 @@ class RbThermal(C.Structure):
 
 class RbAdaptiveRun(C.Structure):
     _fields_ = [("t0", f64), ("t_bound", f64), ("rtol", f64), ("atol", f64), ("t_eval0", f64), ("t_eval_dt", f64),
-                ("n_eval", i64), ("max_steps", i64), ("event_altitude", f64), ("epoch_jd", f64), ("gmst0", f64), ("ephemeris_dt", f64)]
+                ("n_eval", i64), ("max_steps", i64), ("event_altitude", f64), ("epoch_jd", f64), ("gmst0", f64), ("ephemeris_dt", f64),
+                ("method", i32), ("reserved", i32)]
 
 
 class RbAdaptiveOut(C.Structure):
@@ -74,7 +76,7 @@ class RbAdaptiveOut(C.Structure):
 
 class RbStats(C.Structure):
     _fields_ = [("kernel_launches", i64), ("propagate_launches", i64), ("steps_enqueued", i64),
-                ("last_polled_live", i64), ("propagate_ms", f64)]
+                ("last_polled_live", i64), ("propagate_ms", f64), ("sample_bytes_sent", i64)]
 
 
 # every symbol include/reentry_b200.h declares: name -> (restype, argtypes)

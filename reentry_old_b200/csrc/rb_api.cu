@@ -75,7 +75,7 @@ struct rb_ctx {
     cudaStream_t up_stream = nullptr;   // chunked table upload of the packed host path
     double *h_table = nullptr;  // pinned staging for the table
     int64_t h_table_entries = 0;
-    rb_stats stats = {0, 0, 0, -1, 0.0};
+    rb_stats stats = {0, 0, 0, -1, 0.0, 0};
 };
 
 static int32_t cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what) {
@@ -306,8 +306,13 @@ struct LaunchHook {
     virtual int32_t before_launch(int64_t step_end, const cudaStream_t *streams, int n_streams) { (void)step_end; (void)streams; (void)n_streams; return RB_OK; }
     // after the launch that completed `steps_done` steps of the run has been enqueued on all partition streams
     virtual void after_launch(int64_t steps_done, const cudaStream_t *streams, int n_streams) { (void)steps_done; (void)streams; (void)n_streams; }
-    // packed slabs: slab `index` has just been enqueued on `stream` (its kernel is the last thing in the stream)
-    virtual void after_slab(int64_t index, const rb_sample_slab &slab, cudaStream_t stream) { (void)index; (void)slab; (void)stream; }
+    // packed slabs: slab `index` of partition q, written by launch number `launch` (-1: the initial-state slab of k_init),
+    // has just been enqueued on `stream` (its kernel is the last thing in the stream)
+    virtual void after_slab(int64_t index, rb_sample_slab &slab, int q, int64_t launch, cudaStream_t stream) { (void)index; (void)slab; (void)q; (void)launch; (void)stream; }
+    // the host has just learnt (lagged poll) how many trajectories of partition q were alive when launch `launch` started
+    virtual void live_count(int q, int64_t launch, int64_t count) { (void)q; (void)launch; (void)count; }
+    // no more launches will be enqueued
+    virtual void finish_slabs() {}
     virtual ~LaunchHook() {}
 };
 
@@ -385,7 +390,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     const int64_t frame0 = (run->flags & RB_FLAG_RESUME) ? run->first_step : 0;
     if (out->samples && !packed && out->n_out_capacity < (frame0 + run->n_steps) / run->out_stride + 1) return RB_ERR_INVALID_ARG;
     if (packed) *out->n_slabs = 0;
-    ctx->stats = rb_stats{0, 0, 0, -1, 0.0};
+    ctx->stats = rb_stats{0, 0, 0, -1, 0.0, 0};
     if (steps_done_out) *steps_done_out = 0;
     if (n == 0) return RB_OK;
     CK(cudaSetDevice(ctx->device));
@@ -451,7 +456,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
     CK(cudaMemsetAsync(ctx->d_n_live + 8, 0, sizeof(int32_t), stream));  // edge-sample counter of k_refine
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 2;
-    if (packed && hook) hook->after_slab(0, out->slabs[0], stream);
+    if (packed && hook) hook->after_slab(0, out->slabs[0], 0, -1, stream);
     if (profile) CK(cudaEventRecord(ctx->span_ev[0], stream));
     if (n_parts > 1) {  // fork
         CK(cudaEventRecord(ctx->fork_ev, stream));
@@ -480,6 +485,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
                 const int32_t seen = pt.h_poll[slot];
                 if (compact) pt.live_bound = std::min<int64_t>(pt.live_bound, seen);  // the list only shrinks when compacted
                 pt.seen_live = seen;
+                if (hook) hook->live_count(q, launch_idx - 1, seen);   // the count after launch idx-2 = alive at the start of idx-1
                 if (seen == 0) pt.finished = true;
                 seen_total += seen;
             }
@@ -541,7 +547,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
             else launch_step<false>(sp, pt.live_bound, pt.s);
             CK(cudaGetLastError());
             if (slab) {
-                if (hook) hook->after_slab(n_slabs, out->slabs[n_slabs], pt.s);
+                if (hook) hook->after_slab(n_slabs, out->slabs[n_slabs], q, launch_idx, pt.s);
                 ++n_slabs;
             }
             if (via_dma) {
@@ -581,6 +587,7 @@ static int32_t propagate_impl(rb_ctx *ctx, const rb_in *in, const rb_run *run, c
         ++launch_idx;
     }
     if (packed) *out->n_slabs = n_slabs;
+    if (hook) hook->finish_slabs();
     if (n_parts > 1) {  // join
         CK(cudaEventRecord(ctx->join_ev, ctx->aux_stream));
         CK(cudaStreamWaitEvent(stream, ctx->join_ev, 0));
@@ -895,22 +902,56 @@ struct TableFeeder : LaunchHook {
     }
 };
 
-// Every slab leaves for the host as ONE contiguous copy-engine transfer as soon as its launch has finished.
+// Every slab leaves for the host by copy engine as soon as its launch has finished AND the host knows how many of its
+// columns are live: a slab is as wide as the host's (one launch old) view of the live count when its launch was
+// enqueued; one loop iteration later the lagged poll tells the exact count at that launch's start, and the transfer
+// (a 2-D copy: rows of `count` doubles at the slab's pitch) carries the live columns only.  Bytes on the link = valid
+// samples + the columns of lanes that retire inside the launch itself.
 struct SlabSender : TableFeeder {
     const double *d_arena = nullptr;
     double *h_arena = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    static constexpr int RING = 8;
+    struct Pending { rb_sample_slab *slab; int64_t launch; cudaEvent_t ev; };
+    cudaEvent_t ring[2][RING] = {};
+    std::vector<Pending> pending[2];
+    int64_t n_queued[2] = {0, 0};
     int64_t bytes_sent = 0;
-    void after_slab(int64_t index, const rb_sample_slab &sl, cudaStream_t stream) override {
+    void send(const Pending &pd, int64_t cols) {
         if (!h_arena || err != cudaSuccess) return;
-        cudaEvent_t e = ev[index & 1];   // (a wait captures the record made just before it: two events are plenty)
-        cudaError_t r = cudaEventRecord(e, stream);
-        if (r == cudaSuccess) r = cudaStreamWaitEvent(copy_stream, e, 0);
-        const size_t bytes = (size_t)(sl.n_rows * RB_SAMPLE_FIELDS * sl.width) * sizeof(double);
-        if (r == cudaSuccess) r = cudaMemcpyAsync(h_arena + sl.offset, d_arena + sl.offset, bytes, cudaMemcpyDeviceToHost, copy_stream);
+        rb_sample_slab &sl = *pd.slab;
+        cols = std::min<int64_t>(std::max<int64_t>(cols, 0), sl.width);
+        cudaError_t r = cudaStreamWaitEvent(copy_stream, pd.ev, 0);
+        if (r == cudaSuccess && cols > 0)
+            r = cudaMemcpy2DAsync(h_arena + sl.offset, (size_t)sl.width * sizeof(double), d_arena + sl.offset, (size_t)sl.width * sizeof(double),
+                                  (size_t)cols * sizeof(double), (size_t)(sl.n_rows * RB_SAMPLE_FIELDS), cudaMemcpyDeviceToHost, copy_stream);
         if (r != cudaSuccess) err = r;
-        bytes_sent += (int64_t)bytes;
+        bytes_sent += cols * sl.n_rows * RB_SAMPLE_FIELDS * (int64_t)sizeof(double);
+    }
+    void after_slab(int64_t index, rb_sample_slab &sl, int q, int64_t launch, cudaStream_t stream) override {
+        (void)index;
+        if (!h_arena || err != cudaSuccess) return;
+        cudaEvent_t e = ring[q][n_queued[q]++ % RING];   // (at most two slabs of a partition wait at any time)
+        cudaError_t r = cudaEventRecord(e, stream);
+        if (r != cudaSuccess) { err = r; return; }
+        Pending pd{&sl, launch, e};
+        if (launch < 1) send(pd, sl.n_live >= 0 ? sl.n_live : sl.width);   // initial states / first launch: everything is alive
+        else pending[q].push_back(pd);
+    }
+    void live_count(int q, int64_t launch, int64_t count) override {
+        auto &v = pending[q];
+        size_t k = 0;
+        for (; k < v.size() && v[k].launch <= launch; ++k) {
+            if (v[k].launch == launch) v[k].slab->n_live = count;
+            send(v[k], v[k].launch == launch ? count : v[k].slab->width);
+        }
+        v.erase(v.begin(), v.begin() + (long)k);
+    }
+    void finish_slabs() override {   // the last launches: their exact counts never reach the host in time
+        for (int q = 0; q < 2; ++q) {
+            for (auto &pd : pending[q]) send(pd, pd.slab->width);
+            pending[q].clear();
+        }
     }
 };
 }  // namespace
@@ -975,8 +1016,8 @@ int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const
     hook.start();   // the builder thread runs ahead from here on (the upload of y0 below overlaps its first entries)
     hook.d_arena = (const double *)d_arena; hook.h_arena = packed; hook.copy_stream = ctx->copy_stream;
     CK(events.make(&hook.up_ev));
-    CK(events.make(&hook.ev[0]));
-    CK(events.make(&hook.ev[1]));
+    for (int q = 0; q < 2; ++q)
+        for (int i = 0; i < SlabSender::RING; ++i) CK(events.make(&hook.ring[q][i]));
 
     CK(cudaMemcpyAsync(d_y0, y0, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, cs));
     double *d_cd = nullptr, *d_area = nullptr, *d_mass = nullptr;
@@ -1027,7 +1068,8 @@ int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const
     if (rc == RB_OK && e == cudaSuccess && packed && edge > 0) {
         // a grid sample coincided with an event time and was added by k_refine after its slab had been sent
         // (measure-zero case): send the arena again
-        e = cudaMemcpyAsync(packed, d_arena, (size_t)hook.bytes_sent, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        const int64_t used = ns_local ? slabs[ns_local - 1].offset + slabs[ns_local - 1].n_rows * RB_SAMPLE_FIELDS * slabs[ns_local - 1].width : 0;
+        e = cudaMemcpyAsync(packed, d_arena, (size_t)used * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream);
     }
     e2 = cudaStreamSynchronize(ctx->copy_stream);
     if (e == cudaSuccess) e = e2;
@@ -1036,8 +1078,9 @@ int32_t rb_propagate_host_packed(rb_ctx *ctx, int64_t n, const double *y0, const
     e2 = cudaStreamSynchronize(ctx->aux_stream);
     if (e == cudaSuccess) e = e2;
     if (rc == RB_OK && e != cudaSuccess) rc = cuda_fail(ctx, e, "rb_propagate_host_packed");
+    ctx->stats.sample_bytes_sent = hook.bytes_sent;
     if (rc == RB_OK && packed) {
-        for (int64_t i = 1; i < ns_local; ++i) slabs[i].n_live = live[(size_t)i];
+        for (int64_t i = 1; i < ns_local; ++i) slabs[i].n_live = live[(size_t)i];   // (exact, from the device; the lagged polls agree)
         *n_slabs = ns_local;
         if (packed_used) *packed_used = ns_local ? slabs[ns_local - 1].offset + slabs[ns_local - 1].n_rows * RB_SAMPLE_FIELDS * slabs[ns_local - 1].width : 0;
     }
@@ -1099,6 +1142,7 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
     if (in->n < 0 || !in->y0 || !out->final_state || !out->status) return RB_ERR_INVALID_ARG;
     if (!(run->rtol > 0) || !(run->atol >= 0) || !(run->t_bound >= run->t0) || run->n_eval < 0 || run->max_steps < 1)
         return RB_ERR_INVALID_ARG;
+    if (run->method != RB_METHOD_RK45 && run->method != RB_METHOD_RK23) return RB_ERR_INVALID_ARG;
     if (in->n == 0) return RB_OK;
     CK(cudaSetDevice(ctx->device));
     AdaptiveParams p{};
@@ -1127,7 +1171,9 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
         k_eph_nodes<<<(unsigned)((n_nodes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ctx->d_eph, n_nodes, p.eph_t0, run->ephemeris_dt,
                                                                                          run->epoch_jd, run->gmst0);
     }
-    k_adaptive<<<(unsigned)((in->n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p);
+    const unsigned agrid = (unsigned)((in->n + ADAPTIVE_BLOCK - 1) / ADAPTIVE_BLOCK);
+    if (run->method == RB_METHOD_RK23) k_adaptive<1><<<agrid, ADAPTIVE_BLOCK, (RB_ADAPTIVE_K_SHARED ? adaptive_smem_bytes<1>() : 0), (cudaStream_t)stream>>>(p);
+    else k_adaptive<0><<<agrid, ADAPTIVE_BLOCK, (RB_ADAPTIVE_K_SHARED ? adaptive_smem_bytes<0>() : 0), (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
     return RB_OK;
 }

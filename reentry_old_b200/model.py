@@ -10,7 +10,8 @@ CPU fallback: without a CUDA device or without the built library the calls raise
 Fixed-step contract: the reference integrates with scipy's adaptive
 RK45; this path integrates with the same Dormand-Prince tableau at a FIXED step (the spacing
 of `t_eval`, or `max_step`), which is the reference's own stepper with step-size control
-switched off.  `sim_type` other than 'RK45' raises NotImplementedError.
+switched off (`sim_type` must be 'RK45' there).  The adaptive mode -- run_simulation's default, the reference as
+shipped -- also offers 'RK23'; DOP853 / Radau / BDF / LSODA raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -97,7 +98,7 @@ class DeviceContext:
         self.check(self.lib.rb_ctx_stats(self.handle, C.byref(s)))
         return dict(kernel_launches=s.kernel_launches, propagate_launches=s.propagate_launches,
                     steps_enqueued=s.steps_enqueued, last_polled_live=s.last_polled_live,
-                    propagate_ms=s.propagate_ms)
+                    propagate_ms=s.propagate_ms, sample_bytes_sent=s.sample_bytes_sent)
 
     def fp64_peak_tflops(self, ms=200.0):
         torch = _torch()
@@ -235,7 +236,7 @@ class OdeResultLike(dict):
 
 class SpacecraftModel:
     def __init__(self, Cd=2.2, A=20.0, m=500.0, epoch=None, gmst0=0.0, sim_type="RK45",
-                 material=(233, 1, 1, 0.1), dt=10, iter_fact=2, device=None, integrator="fixed"):
+                 material=(233, 1, 1, 0.1), dt=10, iter_fact=2, device=None, integrator="adaptive"):
         # same attributes as spacecraft_model.py:394-410
         self.Cd = Cd
         self.A = A
@@ -254,9 +255,12 @@ class SpacecraftModel:
         self.dt = dt
         self.iter_fact = iter_fact
         self.device = device
+        # integrator of run_simulation: 'adaptive' (default) = scipy's error-controlled RK45 exactly as the reference calls
+        # it (spacecraft_model.py:516) -- what a drop-in user expects; 'fixed' = the fixed-step Dormand-Prince contract of
+        # the ensemble hot path (step = t_eval spacing or max_step).  run_ensemble is always fixed-step.
         if integrator not in ("fixed", "adaptive"):
-            raise ValueError("integrator must be 'fixed' (fixed-step Dormand-Prince, the ensemble hot path) or "
-                             "'adaptive' (scipy's error-controlled RK45 exactly as the reference calls it)")
+            raise ValueError("integrator must be 'adaptive' (scipy's error-controlled RK45 exactly as the reference calls it) "
+                             "or 'fixed' (fixed-step Dormand-Prince, the ensemble hot path)")
         self.integrator = integrator
 
     # ------------------------------------------------------------------------- plumbing
@@ -582,8 +586,8 @@ class SpacecraftModel:
         reference's ephemeris functions at every stage time of every trajectory."""
         torch = _torch()
         ctx = self._ctx()
-        if self.sim_type != "RK45":
-            raise NotImplementedError("only RK45 is implemented on this path")
+        if self.sim_type not in ("RK45", "RK23"):
+            raise NotImplementedError("sim_type must be 'RK45' or 'RK23' (scipy's DOP853 / Radau / BDF / LSODA are not built)")
         t0, tf = float(t_span[0]), float(t_span[1])
         if n_eval is None:
             n_eval = len(np.arange(t0, tf, t_eval_dt))
@@ -608,7 +612,8 @@ class SpacecraftModel:
                      cd_scalar=float(self.Cd), area_scalar=float(self.A), mass_scalar=float(self.m))
         run = L.RbAdaptiveRun(t0=t0, t_bound=tf, rtol=float(rtol), atol=float(atol), t_eval0=t0, t_eval_dt=float(t_eval_dt),
                               n_eval=int(n_eval), max_steps=int(max_steps), event_altitude=float(event_altitude),
-                              epoch_jd=self.epoch, gmst0=self.gmst0, ephemeris_dt=float(ephemeris_dt))
+                              epoch_jd=self.epoch, gmst0=self.gmst0, ephemeris_dt=float(ephemeris_dt),
+                              method=L.RB_METHOD_RK23 if self.sim_type == "RK23" else L.RB_METHOD_RK45)
         out = L.RbAdaptiveOut(samples=None if samples is None else samples.data_ptr(), sample_stride=L.RB_SAMPLE_FIELDS * n,
                               field_stride=n, final_state=final_state.data_ptr(), impact_time=impact_time.data_ptr(),
                               status=status.data_ptr(), n_samples=n_samples.data_ptr(), n_accepted=n_acc.data_ptr(),
@@ -627,7 +632,8 @@ class SpacecraftModel:
 
     # ------------------------------------------------------------------ run_simulation
     def run_simulation(self, t_span, y0, t_eval, progress_callback=None, max_step=None, integrator=None):
-        """spacecraft_model.py:490-519 for ONE trajectory, fixed-step contract.
+        """spacecraft_model.py:490-519 for ONE trajectory.  With the model's default integrator ('adaptive') this is the
+        reference's own adaptive RK45 run; integrator='fixed' (argument or constructor) selects the fixed-step contract:
 
         `t_eval` must be a uniform grid starting at t_span[0] (the app builds
         `np.arange(ts, tf, dt)`, app.py:171); the integration step is its spacing, or `max_step`
@@ -709,7 +715,7 @@ class SpacecraftModel:
         sol.message = ("A termination event occurred." if hit else
                        "The solver successfully reached the end of the integration interval." if sol.success
                        else "Required step size is less than spacing between numbers.")
-        sol.nfev = 2 + 6 * (int(res.n_accepted[0].item()) + int(res.n_rejected[0].item()))
+        sol.nfev = 2 + (3 if self.sim_type == "RK23" else 6) * (int(res.n_accepted[0].item()) + int(res.n_rejected[0].item()))
         sol.njev = 0
         sol.nlu = 0
         sol.sol = None

@@ -12,8 +12,8 @@ import numpy as np
 import pytest
 
 
-def cases(golden_dir):
-    g = np.load(os.path.join(golden_dir, "adaptive.npz"))
+def cases(golden_dir, name="adaptive.npz"):
+    g = np.load(os.path.join(golden_dir, name))
     for k in range(int(g["n_cases"])):
         Cd, A, m, gmst0, tf, dt = g[f"cfg_{k}"]
         yield k, dict(Cd=Cd, A=A, m=m, gmst0=gmst0, tf=tf, dt=dt, y0=g[f"y0_{k}"], t=g[f"t_{k}"], y=g[f"y_{k}"],
@@ -44,6 +44,35 @@ def test_oracle_adaptive_vs_reference(oracle, golden_dir):
         r = oracle.propagate_adaptive(c["y0"], c["Cd"], c["A"], c["m"], c["epoch"], c["gmst0"], (0, c["tf"]), 0.0, c["dt"], n_eval)
         check(k, c, r["t"], r["y"], r["t_event"], r["nfev"], r["n_accepted"])
         assert r["status"] == c["status"]
+
+
+def test_oracle_rk23_vs_reference(oracle, golden_dir):
+    """sim_type='RK23' (app.py:51; spacecraft_model.py:516 passes it to solve_ivp): the oracle's data-driven stepper with
+    scipy's Bogacki-Shampine pair against the unmodified reference's run_simulation (tests/golden/adaptive_rk23.npz)."""
+    for k, c in cases(golden_dir, "adaptive_rk23.npz"):
+        n_eval = len(np.arange(0, c["tf"], c["dt"]))
+        r = oracle.propagate_adaptive(c["y0"], c["Cd"], c["A"], c["m"], c["epoch"], c["gmst0"], (0, c["tf"]), 0.0, c["dt"], n_eval,
+                                      method="RK23", max_steps=1_000_000)
+        check(k, c, r["t"], r["y"], r["t_event"], r["nfev"], r["n_accepted"])
+        assert r["status"] == c["status"]
+
+
+@pytest.mark.gpu
+def test_device_rk23_vs_reference(golden_dir):
+    import torch
+
+    from reentry_old_b200 import SpacecraftModel
+
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    for k, c in cases(golden_dir, "adaptive_rk23.npz"):
+        m = SpacecraftModel(Cd=c["Cd"], A=c["A"], m=c["m"], epoch=c["epoch"], gmst0=c["gmst0"], sim_type="RK23")
+        sol = m.run_simulation((0, c["tf"]), c["y0"], np.arange(0, c["tf"], c["dt"]))     # the reference's call, app.py:190
+        te = sol.t_events[0][0] if len(sol.t_events[0]) else float("nan")
+        check(k, c, sol.t, sol.y, te, sol.nfev, None, exact_counts=False)
+        assert sol.status == c["status"]
+    with pytest.raises(NotImplementedError):
+        SpacecraftModel(sim_type="DOP853").run_simulation((0, 10), np.ones(6) * 7e6, np.arange(0, 10, 1.0))
 
 
 @pytest.mark.gpu

@@ -102,7 +102,7 @@ def test_c1_run_simulation_drop_in(Model, golden_dir):
     m = Model(Cd=1.3, A=14.0, m=5000.0, epoch=float(g["epoch_jd"]), gmst0=0.0)
     y0 = m.get_initial_state(7800, 0, 0, 120e3, 90, -1, gmst=0.0)
     calls = []
-    sol = m.run_simulation((0, 800), y0, np.arange(0, 800, 1.0), progress_callback=lambda p, e: calls.append(p))
+    sol = m.run_simulation((0, 800), y0, np.arange(0, 800, 1.0), progress_callback=lambda p, e: calls.append(p), integrator="fixed")
     assert calls and calls[-1] == 1.0
     assert sol.y.shape == (6, 695) and sol.t.shape == (695,) and sol.t[-1] == 694.0
     assert sol.status == 1 and len(sol.t_events[0]) == 1
@@ -402,7 +402,7 @@ def test_error_codes(Model, torch):
     with pytest.raises(NotImplementedError):
         m.run_ensemble(np.zeros((1, 6)), dt=1.0, n_steps=1)
     with pytest.raises(ValueError):
-        Model().run_simulation((0, 10), np.ones(6), np.array([0.0, 1.0, 3.0]))          # non-uniform t_eval
+        Model().run_simulation((0, 10), np.ones(6), np.array([0.0, 1.0, 3.0]), integrator="fixed")          # non-uniform t_eval
     # zero trajectories / zero steps are valid and empty
     r = Model().run_ensemble(np.zeros((0, 6)), dt=1.0, n_steps=5)
     assert r.samples.shape == (6, 8, 0)
