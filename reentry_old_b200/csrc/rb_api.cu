@@ -630,6 +630,16 @@ int32_t rb_propagate(rb_ctx *ctx, const rb_in *in, const rb_run *run, const rb_o
 }
 
 // ------------------------------------------------------------------ host-buffer path
+struct EventSet {   // events of one call, destroyed on every exit path
+    std::vector<cudaEvent_t> evs;
+    cudaError_t make(cudaEvent_t *e) {
+        cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        if (r == cudaSuccess) evs.push_back(*e);
+        return r;
+    }
+    ~EventSet() { for (auto e : evs) cudaEventDestroy(e); }
+};
+
 static int32_t host_buf(rb_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes > ctx->d_host_bytes[slot]) {
         cudaFree(ctx->d_host_bufs[slot]);
@@ -764,10 +774,11 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
     SampleDownloader dl;
     dl.ctx = ctx; dl.d_samples = (const double *)d_samples; dl.h_samples = samples; dl.n = n;
     dl.out_stride = run->out_stride; dl.copy_stream = ctx->copy_stream;
+    EventSet events;   // (destroyed on every exit path)
     cudaEvent_t ev[2] = {nullptr, nullptr};
     const bool staged = samples && !zero_copy;
     if (staged)
-        for (int q = 0; q < 2; ++q) { CK(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming)); dl.ev[q] = ev[q]; }
+        for (int q = 0; q < 2; ++q) { CK(events.make(&ev[q])); dl.ev[q] = ev[q]; }
     rb_run r2 = *run;
     r2.flags |= RB_FLAG_EARLY_EXIT;
     int64_t steps_done = 0;
@@ -777,9 +788,9 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         if (host_buf(ctx, 7, (size_t)n_out * row, &d_staging) != RB_OK) { (void)cudaGetLastError(); d_staging = nullptr; }   // no room: direct stores only
       if (d_staging) {
         route.staging = (double *)d_staging; route.host = samples; route.copy_stream = ctx->copy_stream;
-        for (int q = 0; q < 2; ++q) { CK(cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming)); route.ev[q] = ev[q]; }
+        for (int q = 0; q < 2; ++q) { CK(events.make(&ev[q])); route.ev[q] = ev[q]; }
         for (int q = 0; q < 2; ++q)
-            for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&route.done[q][i], cudaEventDisableTiming));
+            for (int i = 0; i < 8; ++i) CK(events.make(&route.done[q][i]));
       }
     }
     const auto t_prop = now();
@@ -813,27 +824,18 @@ int32_t rb_propagate_host(rb_ctx *ctx, int64_t n, const double *y0, const double
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "rb_propagate_host download");
     }
+    if (rc != RB_OK) {   // drain: the copy engine may still be writing the caller's buffers
+        cudaStreamSynchronize(cs);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->aux_stream);
+    }
     if (trace) fprintf(stderr, ", download %.2f ms, total %.2f ms\n", ms_since(t_dl), ms_since(t_begin));
-    for (int q = 0; q < 2; ++q)
-        if (ev[q]) cudaEventDestroy(ev[q]);
-    for (int q = 0; q < 2; ++q)
-        for (int i = 0; i < 8; ++i)
-            if (route.done[q][i]) cudaEventDestroy(route.done[q][i]);
     if (n_samples_used) *n_samples_used = !samples ? 0 : (staged ? dl.rows_copied : steps_done / run->out_stride + 1);
     return rc;
 }
 
 // ------------------------------------------------------------------ host-buffer path, packed sample slabs
 namespace {
-struct EventSet {   // events of one call, destroyed on every exit path
-    std::vector<cudaEvent_t> evs;
-    cudaError_t make(cudaEvent_t *e) {
-        cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
-        if (r == cudaSuccess) evs.push_back(*e);
-        return r;
-    }
-    ~EventSet() { for (auto e : evs) cudaEventDestroy(e); }
-};
 
 // The step kernel's table (96-byte entries) is built on the HOST while the GPU already runs, and only as far as
 // launches are actually enqueued: a run "until impact" with a generous step cap pays for the steps it flies.  ONE
@@ -1220,31 +1222,38 @@ int32_t rb_fp64_peak_probe(rb_ctx *ctx, double ms, double *tflops_out, void *str
     CK(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, ctx->device));
-    double *sink;
-    CK(cudaMalloc(&sink, 8));
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a));
-    CK(cudaEventCreate(&b));
+    double *sink = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = prop.multiProcessorCount * 8, block = 256;
-    int iters = 2000;
-    double best = 0.0, elapsed_total = 0.0;
-    k_dfma_peak<<<grid, block, 0, s>>>(sink, 200, 1.0);  // warm-up
-    for (int rep = 0; rep < 50 && elapsed_total < ms; ++rep) {
-        CK(cudaEventRecord(a, s));
-        k_dfma_peak<<<grid, block, 0, s>>>(sink, iters, 1.0 + rep);
-        CK(cudaEventRecord(b, s));
-        CK(cudaEventSynchronize(b));
-        float t = 0;
-        CK(cudaEventElapsedTime(&t, a, b));
-        const double flop = 2.0 * DFMA_PER_THREAD_ITER * (double)iters * grid * block;
-        best = std::max(best, flop / (t * 1e-3) / 1e12);
-        elapsed_total += t;
-        if (t < 5.0f) iters *= 2;
-    }
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    double best = 0.0;
+    auto work = [&]() -> cudaError_t {   // (one exit below frees what was allocated, whatever fails)
+        cudaError_t e = cudaMalloc(&sink, 8);
+        if (e == cudaSuccess) e = cudaEventCreate(&a);
+        if (e == cudaSuccess) e = cudaEventCreate(&b);
+        if (e != cudaSuccess) return e;
+        int iters = 2000;
+        double elapsed_total = 0.0;
+        k_dfma_peak<<<grid, block, 0, s>>>(sink, 200, 1.0);  // warm-up
+        for (int rep = 0; rep < 50 && elapsed_total < ms; ++rep) {
+            if ((e = cudaEventRecord(a, s)) != cudaSuccess) return e;
+            k_dfma_peak<<<grid, block, 0, s>>>(sink, iters, 1.0 + rep);
+            if ((e = cudaEventRecord(b, s)) != cudaSuccess) return e;
+            if ((e = cudaEventSynchronize(b)) != cudaSuccess) return e;
+            float t = 0;
+            if ((e = cudaEventElapsedTime(&t, a, b)) != cudaSuccess) return e;
+            const double flop = 2.0 * DFMA_PER_THREAD_ITER * (double)iters * grid * block;
+            best = std::max(best, flop / (t * 1e-3) / 1e12);
+            elapsed_total += t;
+            if (t < 5.0f) iters *= 2;
+        }
+        return cudaGetLastError();
+    };
+    const cudaError_t e = work();
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
     cudaFree(sink);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "rb_fp64_peak_probe");
     *tflops_out = best;
     return RB_OK;
 }

@@ -83,18 +83,25 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
-// Stage state of stage S from the K rows in shared memory: Ka_j, component c at Kt + (j*3 + c)*BLOCK*8 (Kt = 32-bit
-// shared address of this thread's slot-0 entry; all offsets are immediates of the LDS).  Ka_{S-1} has just been
-// evaluated: it comes in registers (klast) -- the same value its slot holds, three loads fewer.
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double &a, double &b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double a, double b) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+// Stage state of stage S from the K rows in shared memory.  Ka_j is stored as an (x, y) PAIR at kp + j*BLOCK*16 (kp = 32-bit
+// shared address of this thread's pair in slot 0: one 16-byte load) and its z at kz + j*BLOCK*8: two loads per row instead
+// of three; all offsets are immediates of the LDS.  Ka_{S-1} has just been evaluated: it comes in registers (klast) -- the
+// same value its slot holds, no load at all.
 template <int S, int BLOCK>
-__device__ __forceinline__ void stage_state(uint32_t kt, const double y[6], const HTableau &ht, double ys[6], const double klast[3]) {
+__device__ __forceinline__ void stage_state(uint32_t kp, uint32_t kz, const double y[6], const HTableau &ht, double ys[6], const double klast[3]) {
     double k[6][3];
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (j == S - 1) k[j][c] = klast[c];
-            else k[j][c] = lds_f64(kt + (uint32_t)((j * K_ROWS + c) * BLOCK * 8));
+        if (j == S - 1) { k[j][0] = klast[0]; k[j][1] = klast[1]; k[j][2] = klast[2]; }
+        else {
+            lds_f64x2(kp + (uint32_t)(j * BLOCK * 16), k[j][0], k[j][1]);
+            k[j][2] = lds_f64(kz + (uint32_t)(j * BLOCK * 8));
         }
     }
     stage_update<S>(ht, k, y, ys);
@@ -227,8 +234,9 @@ __device__ __noinline__ void nan_rows_at(double *column, int64_t sample_stride, 
     nan_rows_at((p).samples + (first) * (p).sample_stride + (col), (p).sample_stride, (p).field_stride, (last) - (first) + 1)
 
 // ---------------------------------------------------------------- the hot kernel
-// Shared memory per block: [2 x tile][Ka slots: 6 x 3 x BLOCK][y_n backup: 6 x BLOCK][bc, g_old: 2 x BLOCK]
-//                          [lookup-table image, TAB_DOUBLES][2 mbarriers]
+// Shared memory per block: [2 x tile][pairs: Ka (x, y) of 6 slots + y_n as 3 pairs, 9 x BLOCK x 16 B]
+//                          [scalars: Ka z of 6 slots, bc, g_old, 8 x BLOCK x 8 B][lookup-table image, TAB_DOUBLES][2 mbarriers]
+// (same size as 26 rows of BLOCK doubles)
 constexpr int PARK_ROWS = 8;   // per-thread doubles parked in shared memory: y_n[6], bc, g_old
 template <int BLOCK>
 constexpr size_t propagate_smem_bytes() {
@@ -240,8 +248,8 @@ constexpr size_t propagate_smem_bytes() {
 // inlined evaluation with a `switch` over the stage-state arithmetic -- spent ~40 of its ~430 instructions per stage
 // on dispatch (jump table, K-slot select, loop state); a call and a return cost 3.
 //   ent   32-bit shared address of the 96-byte time-table entry of the stage time
-//   park  32-bit shared address of this thread's parked values (bc at row 6)
-//   kdst  32-bit shared address where a[0..2] go (this thread's column of the K slot)
+//   bcp   32-bit shared address of this thread's parked body constant
+//   kdp, kdz  32-bit shared addresses where a[0..1] (one 16-byte store) and a[2] go (this thread's place in the K slot)
 // Returns |r| - R (the event function's altitude) of the evaluated state.
 #ifndef RB_RHS_INLINE
 #define RB_RHS_INLINE 1   // 1 (default): the evaluation is inlined at its seven sites; 0: one subroutine, seven calls.
@@ -257,14 +265,14 @@ constexpr size_t propagate_smem_bytes() {
 //   tabs  32-bit shared address of the block's lookup-table image (rb_math.cuh TabShared)
 //   a     the acceleration, also handed back in registers: the next stage's state uses it without reloading it
 template <int BLOCK, bool SKIP>
-__device__ RB_RHS_LINKAGE double rhs_eval(uint32_t ent, uint32_t park, uint32_t kdst, uint32_t tabs, double x, double y, double z,
-                                        double vx, double vy, double vz, double a[3]) {
+__device__ RB_RHS_LINKAGE double rhs_eval(uint32_t ent, uint32_t bca, uint32_t kdp, uint32_t kdz, uint32_t tabs, double x, double y,
+                                        double z, double vx, double vy, double vz, double a[3]) {
     const double *e = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)ent));
     const double r[3] = {x, y, z}, v[3] = {vx, vy, vz};
-    const double *bcp = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)(park + 6u * BLOCK * 8u)));
+    const double *bcp = reinterpret_cast<const double *>(__cvta_shared_to_generic((size_t)bca));
     double alt;
     acceleration<false, SKIP, TabShared>(e, r, v, bcp, a, nullptr, &alt, TabShared{tabs});
-    sts_f64(kdst, a[0]); sts_f64(kdst + BLOCK * 8, a[1]); sts_f64(kdst + 2 * BLOCK * 8, a[2]);
+    sts_f64x2(kdp, a[0], a[1]); sts_f64(kdz, a[2]);
     return alt;
 }
 
@@ -329,11 +337,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
     }
     // 32-bit shared addresses of this thread's columns, kept opaque so that they live in ONE register each instead of
     // being rebuilt (thread id, shared window base) at every use
-    uint32_t Kt = smem_u32(Ks) + threadIdx.x * 8;     // Ka of slot s, component c at Kt + (s*3 + c)*BLOCK*8
-    asm volatile("" : "+r"(Kt));
-    const uint32_t Pk = Kt + K_SLOTS * K_ROWS * BLOCK * 8;   // parked: y_n[c] at Pk + c*BLOCK*8, bc at row 6, g_old at row 7
-    sts_f64(Pk + 6 * BLOCK * 8, make_body(b_cd, b_area, b_mass).bc);
-    sts_f64(Pk + 7 * BLOCK * 8, event_g(y, p.event_altitude));
+    uint32_t Kp = smem_u32(Ks) + threadIdx.x * 16;    // pairs: Ka (x, y) of slot s at Kp + s*BLOCK*16, y_n pairs at slots 6..8
+    asm volatile("" : "+r"(Kp));
+    uint32_t Kz = smem_u32(Ks) + 9 * BLOCK * 16 + threadIdx.x * 8;   // scalars: Ka z of slot s at Kz + s*BLOCK*8, bc row 6, g_old row 7
+    asm volatile("" : "+r"(Kz));
+    constexpr uint32_t PB = BLOCK * 16, ZB = BLOCK * 8;   // bytes per pair row / per scalar row
+    sts_f64(Kz + 6 * ZB, make_body(b_cd, b_area, b_mass).bc);
+    sts_f64(Kz + 7 * ZB, event_g(y, p.event_altitude));
     // the block's copy of the lookup tables (2^(j/32), atan reference angles, atmosphere layer records)
     for (int j = threadIdx.x; j < TAB_DOUBLES; j += BLOCK)
         Tab[j] = j < TAB_ATAN ? g_exp_tab[j] : (j < TAB_LAYER ? (&g_atan_tab[0][0])[j - TAB_ATAN] : (&g_layer[0][0])[j - TAB_LAYER]);
@@ -357,29 +367,29 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
         uint32_t ent = smem_u32(tiles + (t % TILE_BUFFERS) * TILE_DOUBLES);   // entry 5 m of the tile = t_n of its step m
         const int ts = tile_steps_of(t);
         // the launch's very first evaluation: Ka_0 = a(t_n, y_n) (later steps inherit it from the previous step: FSAL)
-        if (t == 0 && alive) rhs_eval<BLOCK, SKIP>(ent, Pk, Kt, Tb, y[0], y[1], y[2], y[3], y[4], y[5], ka);
+        if (t == 0 && alive) rhs_eval<BLOCK, SKIP>(ent, Kz + 6 * ZB, Kp, Kz, Tb, y[0], y[1], y[2], y[3], y[4], y[5], ka);
         for (int m = 0; m < ts; ++m) {
             if (alive) {
-                constexpr uint32_t EB = HOT_DOUBLES * 8, SB = K_ROWS * BLOCK * 8;   // bytes per table entry / per K slot
+                constexpr uint32_t EB = HOT_DOUBLES * 8;   // bytes per table entry
                 double ys[6];
-                stage_state<1, BLOCK>(Kt, y, p.ht, ys, ka);
-                rhs_eval<BLOCK, SKIP>(ent + 1 * EB, Pk, Kt + 1 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
-                stage_state<2, BLOCK>(Kt, y, p.ht, ys, ka);
-                rhs_eval<BLOCK, SKIP>(ent + 2 * EB, Pk, Kt + 2 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
-                stage_state<3, BLOCK>(Kt, y, p.ht, ys, ka);
-                rhs_eval<BLOCK, SKIP>(ent + 3 * EB, Pk, Kt + 3 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
-                stage_state<4, BLOCK>(Kt, y, p.ht, ys, ka);
-                rhs_eval<BLOCK, SKIP>(ent + 4 * EB, Pk, Kt + 4 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
-                stage_state<5, BLOCK>(Kt, y, p.ht, ys, ka);
-                rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt + 5 * SB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<1, BLOCK>(Kp, Kz, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 1 * EB, Kz + 6 * ZB, Kp + 1 * PB, Kz + 1 * ZB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<2, BLOCK>(Kp, Kz, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 2 * EB, Kz + 6 * ZB, Kp + 2 * PB, Kz + 2 * ZB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<3, BLOCK>(Kp, Kz, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 3 * EB, Kz + 6 * ZB, Kp + 3 * PB, Kz + 3 * ZB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<4, BLOCK>(Kp, Kz, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 4 * EB, Kz + 6 * ZB, Kp + 4 * PB, Kz + 4 * ZB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
+                stage_state<5, BLOCK>(Kp, Kz, y, p.ht, ys, ka);
+                rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Kz + 6 * ZB, Kp + 5 * PB, Kz + 5 * ZB, Tb, ys[0], ys[1], ys[2], ys[3], ys[4], ys[5], ka);
 #pragma unroll
-                for (int c = 0; c < 6; ++c) sts_f64(Pk + c * BLOCK * 8, y[c]);
-                stage_state<6, BLOCK>(Kt, y, p.ht, ys, ka);
+                for (int c = 0; c < 3; ++c) sts_f64x2(Kp + (6 + c) * PB, y[2 * c], y[2 * c + 1]);
+                stage_state<6, BLOCK>(Kp, Kz, y, p.ht, ys, ka);
 #pragma unroll
                 for (int c = 0; c < 6; ++c) y[c] = ys[c];
-                const double alt_new = rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Pk, Kt, Tb, y[0], y[1], y[2], y[3], y[4], y[5], ka);
+                const double alt_new = rhs_eval<BLOCK, SKIP>(ent + 5 * EB, Kz + 6 * ZB, Kp, Kz, Tb, y[0], y[1], y[2], y[3], y[4], y[5], ka);
                 const double g_new = alt_new - p.event_altitude;
-                const double g_old = lds_f64(Pk + 7 * BLOCK * 8);
+                const double g_old = lds_f64(Kz + 7 * ZB);
                 const int64_t step_abs = p.table_step0 + (int64_t)t * TILE_STEPS + m + 1;
                 const bool finite = (__double2hiint(alt_new) & 0x7ff00000) != 0x7ff00000;
                 const bool hit = g_old >= 0.0 && g_new <= 0.0;
@@ -388,7 +398,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                     p.status[tid] = finite ? RB_TRAJ_IMPACTED : RB_TRAJ_NONFINITE;
                     if (p.impact_step) p.impact_step[tid] = (int32_t)step_abs;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) y[c] = lds_f64(Pk + c * BLOCK * 8);
+                    for (int c = 0; c < 3; ++c) lds_f64x2(Kp + (6 + c) * PB, y[2 * c], y[2 * c + 1]);
                     if (p.packed && p.samples) {
                         if (finite && to_sample == 1) {
                             p.edge_slot[2 * (int64_t)tid] = p.slab_offset + (next_k - p.sample_row0) * p.sample_stride + RB_SAMPLE_COL();
@@ -397,7 +407,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParam
                         nan_rows(p, RB_SAMPLE_COL(), next_k, p.k_last);
                     }
                 } else {
-                    sts_f64(Pk + 7 * BLOCK * 8, g_new);
+                    sts_f64(Kz + 7 * ZB, g_new);
                     if (to_sample == 1 && p.samples) {
                         double *sp = p.samples + next_k * p.sample_stride + RB_SAMPLE_COL();
 #pragma unroll

@@ -49,6 +49,7 @@ struct Consts {
     double omega, neg_mu, j2f, j2c, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc, latc_rad;
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double sig_c, top_c;         // sig_ks sig_x0 ; -top_k top_h  (the exponents as one fma of the altitude)
+    double sea_rho;
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
     double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
@@ -92,6 +93,7 @@ static_assert(rb_hi_word_(90000.0) == 0x40F5F900 && rb_hi_word_(1.0) == 0x3FF000
      RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
      (RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS) * RB_SIGMOID_X0, -(rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT) * rb_bp_(7),   \
+     RB_SEA_LEVEL_RHO,                                                                               \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
      RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_), RB_L8_(rb_bphi_)}
 
@@ -261,16 +263,9 @@ template <class TB = TabGlobal>
 RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out, const TB &tb = TB()) {
     // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
     // solar_m1 = solar_time - 1 (both from the time table)
-    if (altitude <= 0.0) {   // (below the ellipsoid's equatorial radius: never on a live trajectory's hot path, so the
-#if defined(__CUDA_ARCH__)   //  constant is formed HERE -- a volatile asm cannot be hoisted above the branch)
-        double sea;
-        asm volatile("mov.f64 %0, 0d3FF399999999999A;" : "=d"(sea));   // RB_SEA_LEVEL_RHO = 1.225
-        T_out = RB_SEA_LEVEL_T;
-        return sea;
-#else
-        T_out = RB_SEA_LEVEL_T;
-        return RB_SEA_LEVEL_RHO;
-#endif
+    if (altitude <= 0.0) {   // at or below the sphere of the equatorial radius (never on a live reentry's hot path): the
+        T_out = RB_SEA_LEVEL_T;  // constant comes from the constant bank -- as a literal the compiler materialises it with
+        return KC(sea_rho);      // two predicated moves in front of the branch of every evaluation
     }
     double factor = solar_time;
     // From here on altitude > 0 (or NaN): the thresholds (90 km, the layer breakpoints) have zero low words, so
