@@ -270,13 +270,14 @@ typedef struct rb_adaptive_run {
     double ephemeris_dt;         /* 0: Sun / Moon / solar factor evaluated at every stage time, as the reference does;
                                     > 0: evaluated on a grid of this spacing (seconds, on the device) and interpolated
                                     (4-point Lagrange; error 3e-11 m on the Moon's position at 16 s): faster ensembles */
-    int32_t method;              /* RB_METHOD_RK45 (the reference's default sim_type) or RB_METHOD_RK23: solve_ivp's `method`,
-                                    which run_simulation takes from SpacecraftModel.sim_type (spacecraft_model.py:516; the app's
-                                    solver list, app.py:51).  DOP853 / Radau / BDF / LSODA are not built */
+    int32_t method;              /* RB_METHOD_RK45 (the reference's default sim_type), RB_METHOD_RK23 or RB_METHOD_DOP853: solve_ivp's
+                                    `method`, which run_simulation takes from SpacecraftModel.sim_type (spacecraft_model.py:516; the
+                                    app's solver list, app.py:51).  The implicit ones (Radau / BDF / LSODA) are not built */
     int32_t reserved;
 } rb_adaptive_run;
 #define RB_METHOD_RK45 0
 #define RB_METHOD_RK23 1
+#define RB_METHOD_DOP853 2
 
 typedef struct rb_adaptive_out {
     double *samples;             /* [n_eval][8][n] via sample_stride / field_stride, or NULL */

@@ -23,6 +23,7 @@ Everything written here is an OUTPUT OF THE REFERENCE'S OWN CODE:
                        spacecraft_temperature calls
   adaptive.npz         N4: run_simulation as shipped (scipy adaptive RK45) on four launch geometries
   adaptive_rk23.npz    the same with sim_type='RK23' (scipy's Bogacki-Shampine 3(2) pair)
+  adaptive_dop853.npz  the same with sim_type='DOP853', plus the reference's sensitivity to a 1e-14 change of y0
   recorded_trajectory.json   first samples of the trajectory embedded in temperature_model.py:104-105
 
     python oracle/make_golden.py        # ~2-3 min (numba JIT of the reference leaves dominates)
@@ -349,6 +350,17 @@ def adaptive(sm, const, sim_type="RK45"):
                     f"y_event_{k}": (sol.y_events[0][0] if len(te) else np.full(6, np.nan)),
                     f"nfev_{k}": sol.nfev, f"status_{k}": sol.status, f"steps_t_{k}": s2.t,
                     f"altitude_{k}": sol.additional_data["altitude"]})
+        if sim_type == "DOP853":
+            # The reference against ITSELF with the initial state moved by one part in 1e14 (a few ulp): over its first
+            # microsecond steps the 8th-order error estimate is pure rounding noise, so the step sequence -- and, across the
+            # atmosphere model's layer boundaries, the result -- moves by far more than rounding.  Recorded as the
+            # yardstick for the parity bar of this method (tests/test_adaptive.py).
+            sp = mdl.run_simulation((0, tf), y0 * (1 + 1e-14), t_eval)
+            n = min(sol.y.shape[1], sp.y.shape[1])
+            out[f"self_pos_{k}"] = float(np.max(np.linalg.norm(sp.y[:3, :n] - sol.y[:3, :n], axis=0) / np.linalg.norm(sol.y[:3, :n], axis=0)))
+            out[f"self_vel_{k}"] = float(np.max(np.linalg.norm(sp.y[3:, :n] - sol.y[3:, :n], axis=0) / np.linalg.norm(sol.y[3:, :n], axis=0)))
+            out[f"self_te_{k}"] = float(abs(sp.t_events[0][0] - te[0])) if len(te) and len(sp.t_events[0]) else 0.0
+            out[f"self_nfev_{k}"] = int(sp.nfev)
     out["epoch_jd"] = EPOCH_JD
     out["sim_type"] = sim_type
     return out
@@ -373,6 +385,9 @@ def main():
     sm, cc, const = R.load()
     if "--only-adaptive" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "adaptive.npz"), **adaptive(sm, const))
+        return
+    if "--only-dop853" in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "adaptive_dop853.npz"), **adaptive(sm, const, "DOP853"))
         return
     if "--only-rk23" in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "adaptive_rk23.npz"), **adaptive(sm, const, "RK23"))

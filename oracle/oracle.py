@@ -260,7 +260,7 @@ def propagate_adaptive(y0, Cd, A, m, epoch_jd, gmst0, t_span, t_eval0, t_eval_dt
     step_t = np.full(max_steps + 1, np.nan)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
     lib().rbo_propagate_adaptive_method.restype = C.c_int
-    st = lib().rbo_propagate_adaptive_method(C.c_int({"RK45": 0, "RK23": 1}[method]), P(y0), C.c_double(Cd), C.c_double(A), C.c_double(m), C.c_double(epoch_jd),
+    st = lib().rbo_propagate_adaptive_method(C.c_int({"RK45": 0, "RK23": 1, "DOP853": 2}[method]), P(y0), C.c_double(Cd), C.c_double(A), C.c_double(m), C.c_double(epoch_jd),
                                       C.c_double(gmst0), C.c_double(t_span[0]), C.c_double(t_span[1]), C.c_double(rtol),
                                       C.c_double(atol), C.c_double(t_eval0), C.c_double(t_eval_dt), C.c_int64(n_eval), P(samples),
                                       C.byref(ns), C.byref(te), ye, C.byref(na), C.byref(nr), C.byref(nf), P(step_t),

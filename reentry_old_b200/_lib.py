@@ -22,7 +22,7 @@ RB_FLAG_DIRECT_SAMPLES = 128
 RB_FLAG_RESUME = 256
 RB_FLAG_PACKED_SAMPLES = 512
 RB_ABI_VERSION = 2
-RB_METHOD_RK45, RB_METHOD_RK23 = 0, 1
+RB_METHOD_RK45, RB_METHOD_RK23, RB_METHOD_DOP853 = 0, 1, 2
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
 RB_DIAG_FIELDS = 23

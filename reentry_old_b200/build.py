@@ -16,7 +16,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libreentry_b200.so")
 SOURCES = [os.path.join(CSRC, "rb_api.cu")]
 DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + \
-    [os.path.join(ROOT, "include", "reentry_b200.h"), os.path.join(ROOT, "include", "reentry_constants.h")]
+    [os.path.join(ROOT, "include", "reentry_b200.h"), os.path.join(ROOT, "include", "reentry_constants.h"),
+     os.path.join(ROOT, "include", "rb_dop853_tables.h")]
 
 
 def nvcc_path() -> str:

@@ -1144,7 +1144,7 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
     if (in->n < 0 || !in->y0 || !out->final_state || !out->status) return RB_ERR_INVALID_ARG;
     if (!(run->rtol > 0) || !(run->atol >= 0) || !(run->t_bound >= run->t0) || run->n_eval < 0 || run->max_steps < 1)
         return RB_ERR_INVALID_ARG;
-    if (run->method != RB_METHOD_RK45 && run->method != RB_METHOD_RK23) return RB_ERR_INVALID_ARG;
+    if (run->method < RB_METHOD_RK45 || run->method > RB_METHOD_DOP853) return RB_ERR_INVALID_ARG;
     if (in->n == 0) return RB_OK;
     CK(cudaSetDevice(ctx->device));
     AdaptiveParams p{};
@@ -1174,7 +1174,8 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
                                                                                          run->epoch_jd, run->gmst0);
     }
     const unsigned agrid = (unsigned)((in->n + ADAPTIVE_BLOCK - 1) / ADAPTIVE_BLOCK);
-    if (run->method == RB_METHOD_RK23) k_adaptive<1><<<agrid, ADAPTIVE_BLOCK, (RB_ADAPTIVE_K_SHARED ? adaptive_smem_bytes<1>() : 0), (cudaStream_t)stream>>>(p);
+    if (run->method == RB_METHOD_DOP853) k_adaptive<2><<<agrid, ADAPTIVE_BLOCK, (RB_ADAPTIVE_K_SHARED ? adaptive_smem_bytes<2>() : 0), (cudaStream_t)stream>>>(p);
+    else if (run->method == RB_METHOD_RK23) k_adaptive<1><<<agrid, ADAPTIVE_BLOCK, (RB_ADAPTIVE_K_SHARED ? adaptive_smem_bytes<1>() : 0), (cudaStream_t)stream>>>(p);
     else k_adaptive<0><<<agrid, ADAPTIVE_BLOCK, (RB_ADAPTIVE_K_SHARED ? adaptive_smem_bytes<0>() : 0), (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
     return RB_OK;

@@ -24,6 +24,9 @@
 #include <cuda_runtime.h>
 #include <float.h>
 
+#include <type_traits>
+
+#include "rb_dop853_tables.h"
 #include "reentry_b200.h"
 #include "rb_physics.cuh"
 
@@ -573,7 +576,8 @@ struct Dense {
 };
 
 // Brent's root finder with scipy's tolerances (xtol = rtol = 4 eps, ivp.py:76-77)
-__device__ __noinline__ double brent_event(const Dense &d, double xa, double xb) {
+template <class DenseT>
+__device__ __noinline__ double brent_event(const DenseT &d, double xa, double xb) {
     const double xtol = 4 * DBL_EPSILON, rtol = 4 * DBL_EPSILON;
     double xpre = xa, xcur = xb, xblk = 0., fblk = 0., spre = 0., scur = 0.;
     double fpre = d.g(xpre), fcur = d.g(xcur);
@@ -988,12 +992,43 @@ __constant__ RkMethod c_rk[2] = {
      {5.0 / 72, -1.0 / 12, -1.0 / 9, 1.0 / 8}, {{1, -4.0 / 3, 5.0 / 9}, {0, 1, -2.0 / 3}, {0, 4.0 / 3, -8.0 / 9}, {0, -1, 1}},
      -1.0 / 3, 1.0 / 3}};
 template <int METHOD> struct RkShape;
-template <> struct RkShape<0> { static constexpr int S = 6, NP = 4; };   // RK45: 6 stages + FSAL, quartic dense output
-template <> struct RkShape<1> { static constexpr int S = 3, NP = 3; };   // RK23: 3 stages + FSAL, cubic dense output
+template <> struct RkShape<0> { static constexpr int S = 6, NP = 4, KROWS = 7; };    // RK45: 6 stages + FSAL, quartic dense output
+template <> struct RkShape<1> { static constexpr int S = 3, NP = 3, KROWS = 4; };    // RK23: 3 stages + FSAL, cubic dense output
+template <> struct RkShape<2> { static constexpr int S = 12, NP = 0, KROWS = 16; };  // DOP853: 12 stages + FSAL + 3 for the dense output
+
+// Method 2: scipy's DOP853 (rk.py class DOP853; coefficients dop853_coefficients.py -> include/rb_dop853_tables.h).  The error
+// norm combines a 5th- and a 3rd-order estimate (_estimate_error_norm); the order-7 dense output (_dense_output_impl) costs three
+// more RHS evaluations and solve_ivp builds it on EVERY accepted step of the reference's call, because run_simulation's
+// progress_event (spacecraft_model.py:505-511) returns 0, i.e. is "active" on every step (ivp.py:677-681).
+struct DopTables {
+    double C[16], A[16][15], E3[13], E5[13], D[4][16];
+};
+__constant__ DopTables c_dop = {RB_DOP_C_INIT, RB_DOP_A_INIT, RB_DOP_E3_INIT, RB_DOP_E5_INIT, RB_DOP_D_INIT};
+
+struct DenseDop {   // Dop853DenseOutput, rk.py:740-757
+    double F[7][6];
+    double y_old[6];
+    double t_old, h, event_altitude;
+    __device__ void eval(double t, double yo[6]) const {
+        const double x = (t - t_old) / h, x1 = 1 - x;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double a = F[6][c] * x;
+            a = (a + F[5][c]) * x1; a = (a + F[4][c]) * x; a = (a + F[3][c]) * x1;
+            a = (a + F[2][c]) * x; a = (a + F[1][c]) * x1; a = (a + F[0][c]) * x;
+            yo[c] = a + y_old[c];
+        }
+    }
+    __device__ double g(double t) const {
+        double yo[6];
+        eval(t, yo);
+        return event_g(yo, event_altitude);
+    }
+};
 
 constexpr int ADAPTIVE_BLOCK = 64;
 template <int METHOD>
-constexpr size_t adaptive_smem_bytes() { return sizeof(double) * (RkShape<METHOD>::S + 1) * 6 * ADAPTIVE_BLOCK; }
+constexpr size_t adaptive_smem_bytes() { return sizeof(double) * RkShape<METHOD>::KROWS * 6 * ADAPTIVE_BLOCK; }
 
 // The stage derivatives K_0 .. K_S: a local array (default; a 672-byte stack frame, of which the compiler keeps what it can
 // in its 168 registers) or, with RB_ADAPTIVE_K_SHARED = 1, shared memory ([stage][component][thread], conflict-free, 352-byte
@@ -1004,16 +1039,21 @@ constexpr size_t adaptive_smem_bytes() { return sizeof(double) * (RkShape<METHOD
 #endif
 template <int METHOD>
 __global__ void __launch_bounds__(ADAPTIVE_BLOCK, 6) k_adaptive(const AdaptiveParams p) {   // 6 blocks: 168 registers (8: 128 registers and 316 B of spills)
-    constexpr int S = RkShape<METHOD>::S, NP = RkShape<METHOD>::NP;
+    constexpr int S = RkShape<METHOD>::S, NP = RkShape<METHOD>::NP, KROWS = RkShape<METHOD>::KROWS;
+    constexpr bool DOP = METHOD == 2;
     extern __shared__ __align__(16) double Ksh[];
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= p.n) return;
-    const RkMethod &M = c_rk[METHOD];
+    const RkMethod &M = c_rk[DOP ? 0 : METHOD];
+    const double err_exp = DOP ? -1.0 / 8 : M.err_exp, init_exp = DOP ? 1.0 / 8 : M.init_exp;   // error_estimator_order 7 for DOP853
+    auto coef_a = [&](int st, int j) { return DOP ? c_dop.A[st][j] : M.A[st][j]; };
+    auto coef_c = [&](int st) { return DOP ? c_dop.C[st] : M.C[st]; };
+    auto coef_b = [&](int j) { return DOP ? c_dop.A[12][j] : M.B[j]; };
 #if RB_ADAPTIVE_K_SHARED
     double *Kt = Ksh + threadIdx.x;
 #define RB_K(j, i) Kt[((j) * 6 + (i)) * ADAPTIVE_BLOCK]
 #else
-    double Kloc[S + 1][6];
+    double Kloc[KROWS][6];
 #define RB_K(j, i) Kloc[j][i]
 #endif
     const Body body = make_body(p.cd ? p.cd[tid] : p.cd_s, p.area ? p.area[tid] : p.area_s, p.mass ? p.mass[tid] : p.mass_s);
@@ -1047,7 +1087,7 @@ __global__ void __launch_bounds__(ADAPTIVE_BLOCK, 6) k_adaptive(const AdaptivePa
             rhs(t + h0, y1, f1);
             for (int i = 0; i < 6; ++i) a[i] = (f1[i] - f[i]) / scale[i];
             const double d2 = rms6(a) / h0;
-            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), M.init_exp);
+            const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), init_exp);
             h_abs = fmin(fmin(100 * h0, h1), interval);
         }
     }
@@ -1075,59 +1115,104 @@ __global__ void __launch_bounds__(ADAPTIVE_BLOCK, 6) k_adaptive(const AdaptivePa
             for (int s = 1; s < S; ++s) {   // rk_step, rk.py:61-65
                 double ys[6], ks[6];
                 for (int i = 0; i < 6; ++i) {
-                    double dy = M.A[s][0] * RB_K(0, i);
-                    for (int j = 1; j < s; ++j) dy = fma(M.A[s][j], RB_K(j, i), dy);
+                    double dy = coef_a(s, 0) * RB_K(0, i);
+                    for (int j = 1; j < s; ++j) dy = fma(coef_a(s, j), RB_K(j, i), dy);
                     ys[i] = fma(dy, h, y[i]);
                 }
-                rhs(t + M.C[s] * h, ys, ks);
+                rhs(t + coef_c(s) * h, ys, ks);
                 for (int i = 0; i < 6; ++i) RB_K(s, i) = ks[i];
             }
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                double sacc = M.B[0] * RB_K(0, i);
+                double sacc = coef_b(0) * RB_K(0, i);
 #pragma unroll
-                for (int j = 1; j < S; ++j) sacc = fma(M.B[j], RB_K(j, i), sacc);
+                for (int j = 1; j < S; ++j) sacc = fma(coef_b(j), RB_K(j, i), sacc);
                 ynew[i] = fma(h, sacc, y[i]);
             }
             rhs(t + h, ynew, fnew);
-            double en[6];
+            double error_norm;
+            if constexpr (DOP) {   // DOP853._estimate_error_norm
+                double e5n = 0.0, e3n = 0.0;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                RB_K(S, i) = fnew[i];
-                double e = RB_K(0, i) * M.E[0];
+                for (int i = 0; i < 6; ++i) {
+                    RB_K(S, i) = fnew[i];
+                    double e5 = RB_K(0, i) * c_dop.E5[0], e3 = RB_K(0, i) * c_dop.E3[0];
 #pragma unroll
-                for (int j = 1; j < S; ++j) e = fma(RB_K(j, i), M.E[j], e);
-                e = fma(fnew[i], M.E[S], e);
-                const double scale = p.atol + fmax(fabs(y[i]), fabs(ynew[i])) * p.rtol;
-                en[i] = e * h / scale;
+                    for (int j = 1; j <= S; ++j) { e5 = fma(RB_K(j, i), c_dop.E5[j], e5); e3 = fma(RB_K(j, i), c_dop.E3[j], e3); }
+                    const double scale = p.atol + fmax(fabs(y[i]), fabs(ynew[i])) * p.rtol;
+                    e5 /= scale; e3 /= scale;
+                    e5n = fma(e5, e5, e5n); e3n = fma(e3, e3, e3n);
+                }
+                error_norm = (e5n == 0 && e3n == 0) ? 0.0 : fabs(h) * e5n / sqrt((e5n + 0.01 * e3n) * 6.0);
+            } else {
+                double en[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    RB_K(S, i) = fnew[i];
+                    double e = RB_K(0, i) * M.E[0];
+#pragma unroll
+                    for (int j = 1; j < S; ++j) e = fma(RB_K(j, i), M.E[j], e);
+                    e = fma(fnew[i], M.E[S], e);
+                    const double scale = p.atol + fmax(fabs(y[i]), fabs(ynew[i])) * p.rtol;
+                    en[i] = e * h / scale;
+                }
+                error_norm = rms6(en);
             }
-            const double error_norm = rms6(en);
             if (error_norm < 1) {
-                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, M.err_exp));
+                double factor = (error_norm == 0) ? 10.0 : fmin(10.0, 0.9 * pow(error_norm, err_exp));
                 if (rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
                 break;
             }
             if (!(error_norm >= 1)) { failed = true; status = RB_TRAJ_NONFINITE; break; }   // NaN error norm
-            h_abs *= fmax(0.2, 0.9 * pow(error_norm, M.err_exp));
+            h_abs *= fmax(0.2, 0.9 * pow(error_norm, err_exp));
             rejected = true;
             ++rej;
         }
         if (failed) { if (status == RB_TRAJ_ALIVE) status = RB_TRAJ_STEP_FAILED; break; }
         ++acc;
-        Dense d;   // dense output of the accepted step: Q = K^T P (rk.py:173), NP columns
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double q = 0.0;
-                if (k < NP) {
-#pragma unroll
-                    for (int j = 0; j <= S; ++j) q += RB_K(j, c) * M.P[j][k];
+        typename std::conditional<DOP, DenseDop, Dense>::type d;
+        if constexpr (DOP) {   // _dense_output_impl: stages 13..15, then F
+#pragma unroll 1
+            for (int s = S + 1; s < 16; ++s) {
+                double ys[6], ks[6];
+                for (int i = 0; i < 6; ++i) {
+                    double dy = c_dop.A[s][0] * RB_K(0, i);
+                    for (int j = 1; j < s; ++j) dy = fma(c_dop.A[s][j], RB_K(j, i), dy);
+                    ys[i] = fma(dy, h, y[i]);
                 }
-                d.Q[c][k] = q;
+                rhs(t + c_dop.C[s] * h, ys, ks);
+                for (int i = 0; i < 6; ++i) RB_K(s, i) = ks[i];
             }
-            d.y_old[c] = y[c];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double delta = ynew[c] - y[c];
+                d.F[0][c] = delta;
+                d.F[1][c] = h * RB_K(0, c) - delta;
+                d.F[2][c] = 2 * delta - h * (fnew[c] + RB_K(0, c));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double q = c_dop.D[k][0] * RB_K(0, c);
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) q = fma(c_dop.D[k][j], RB_K(j, c), q);
+                    d.F[3 + k][c] = h * q;
+                }
+                d.y_old[c] = y[c];
+            }
+        } else {   // dense output of the accepted step: Q = K^T P (rk.py:173), NP columns
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double q = 0.0;
+                    if (k < NP) {
+#pragma unroll
+                        for (int j = 0; j <= S; ++j) q += RB_K(j, c) * M.P[j][k];
+                    }
+                    d.Q[c][k] = q;
+                }
+                d.y_old[c] = y[c];
+            }
         }
         d.t_old = t; d.h = h; d.event_altitude = p.event_altitude;
         const double g_new = event_g(ynew, p.event_altitude);

@@ -11,7 +11,7 @@ Fixed-step contract: the reference integrates with scipy's
 RK45; this path integrates with the same Dormand-Prince tableau at a FIXED step (the spacing
 of `t_eval`, or `max_step`), which is the reference's own stepper with step-size control
 switched off (`sim_type` must be 'RK45' there).  The adaptive mode -- run_simulation's default, the reference as
-shipped -- also offers 'RK23'; DOP853 / Radau / BDF / LSODA raise NotImplementedError.
+shipped -- also offers 'RK23' and 'DOP853'; the implicit Radau / BDF / LSODA raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -586,8 +586,8 @@ class SpacecraftModel:
         reference's ephemeris functions at every stage time of every trajectory."""
         torch = _torch()
         ctx = self._ctx()
-        if self.sim_type not in ("RK45", "RK23"):
-            raise NotImplementedError("sim_type must be 'RK45' or 'RK23' (scipy's DOP853 / Radau / BDF / LSODA are not built)")
+        if self.sim_type not in ("RK45", "RK23", "DOP853"):
+            raise NotImplementedError("sim_type must be 'RK45', 'RK23' or 'DOP853' (scipy's implicit Radau / BDF / LSODA are not built)")
         t0, tf = float(t_span[0]), float(t_span[1])
         if n_eval is None:
             n_eval = len(np.arange(t0, tf, t_eval_dt))
@@ -613,7 +613,7 @@ class SpacecraftModel:
         run = L.RbAdaptiveRun(t0=t0, t_bound=tf, rtol=float(rtol), atol=float(atol), t_eval0=t0, t_eval_dt=float(t_eval_dt),
                               n_eval=int(n_eval), max_steps=int(max_steps), event_altitude=float(event_altitude),
                               epoch_jd=self.epoch, gmst0=self.gmst0, ephemeris_dt=float(ephemeris_dt),
-                              method=L.RB_METHOD_RK23 if self.sim_type == "RK23" else L.RB_METHOD_RK45)
+                              method={"RK45": L.RB_METHOD_RK45, "RK23": L.RB_METHOD_RK23, "DOP853": L.RB_METHOD_DOP853}[self.sim_type])
         out = L.RbAdaptiveOut(samples=None if samples is None else samples.data_ptr(), sample_stride=L.RB_SAMPLE_FIELDS * n,
                               field_stride=n, final_state=final_state.data_ptr(), impact_time=impact_time.data_ptr(),
                               status=status.data_ptr(), n_samples=n_samples.data_ptr(), n_accepted=n_acc.data_ptr(),
@@ -715,7 +715,11 @@ class SpacecraftModel:
         sol.message = ("A termination event occurred." if hit else
                        "The solver successfully reached the end of the integration interval." if sol.success
                        else "Required step size is less than spacing between numbers.")
-        sol.nfev = 2 + (3 if self.sim_type == "RK23" else 6) * (int(res.n_accepted[0].item()) + int(res.n_rejected[0].item()))
+        n_acc, n_rej = int(res.n_accepted[0].item()), int(res.n_rejected[0].item())
+        if self.sim_type == "DOP853":   # 12 evaluations per attempt + 3 for the dense output of every accepted step
+            sol.nfev = 2 + 12 * (n_acc + n_rej) + 3 * n_acc
+        else:
+            sol.nfev = 2 + (3 if self.sim_type == "RK23" else 6) * (n_acc + n_rej)
         sol.njev = 0
         sol.nlu = 0
         sol.sol = None
