@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 2
+#define RB_ABI_VERSION 3
 #define RB_TABLE_ENTRY_DOUBLES 16 /* one time-table entry = 128 B */
 #define RB_STAGES_PER_STEP 5      /* distinct new stage times per DP5 step (c = 1/5, 3/10, 4/5, 8/9, 1) */
 #define RB_SAMPLE_FIELDS 8        /* x, y, z, vx, vy, vz, altitude, speed */
@@ -286,6 +286,12 @@ typedef struct rb_adaptive_out {
     double *impact_time;         /* [n] NaN = none, or NULL */
     uint8_t *status;             /* [n] REQUIRED */
     int32_t *n_samples, *n_accepted, *n_rejected; /* [n] or NULL */
+    double *step_log;            /* [step_capacity][7][n] or NULL: start time and start state (t_old, y_old[6]) of every ACCEPTED
+                                    step -- the roots and states solve_ivp reports for run_simulation's progress_event
+                                    (spacecraft_model.py:505-511: it returns 0 on every step, so each step is an "event" whose
+                                    root is the step's start, ivp.py:677-699) = sol.t_events[1] / sol.y_events[1].  Steps beyond
+                                    the capacity are not logged (n_accepted still counts them) */
+    int64_t step_capacity;
 } rb_adaptive_out;
 
 int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_run *run, const rb_adaptive_out *out,

@@ -21,7 +21,7 @@ RB_FLAG_STAGED_SAMPLES = 64
 RB_FLAG_DIRECT_SAMPLES = 128
 RB_FLAG_RESUME = 256
 RB_FLAG_PACKED_SAMPLES = 512
-RB_ABI_VERSION = 2
+RB_ABI_VERSION = 3
 RB_METHOD_RK45, RB_METHOD_RK23, RB_METHOD_DOP853 = 0, 1, 2
 RB_TABLE_ENTRY_DOUBLES = 16
 RB_SAMPLE_FIELDS = 8
@@ -71,7 +71,7 @@ class RbAdaptiveRun(C.Structure):
 
 class RbAdaptiveOut(C.Structure):
     _fields_ = [("samples", vp), ("sample_stride", i64), ("field_stride", i64), ("final_state", vp), ("impact_time", vp),
-                ("status", vp), ("n_samples", vp), ("n_accepted", vp), ("n_rejected", vp)]
+                ("status", vp), ("n_samples", vp), ("n_accepted", vp), ("n_rejected", vp), ("step_log", vp), ("step_capacity", i64)]
 
 
 class RbStats(C.Structure):

@@ -1158,6 +1158,8 @@ int32_t rb_propagate_adaptive(rb_ctx *ctx, const rb_in *in, const rb_adaptive_ru
     p.samples = out->samples; p.sample_stride = out->sample_stride; p.field_stride = out->field_stride;
     p.final_state = out->final_state; p.impact_time = out->impact_time; p.status = out->status;
     p.n_samples = out->n_samples; p.n_accepted = out->n_accepted; p.n_rejected = out->n_rejected;
+    if (out->step_log && out->step_capacity < 0) return RB_ERR_INVALID_ARG;
+    p.step_log = out->step_log; p.step_capacity = out->step_log ? out->step_capacity : 0;
     if (run->ephemeris_dt > 0.0) {   // time-only inputs from a grid (built on the device) instead of at every stage time
         const double span = run->t_bound - run->t0;
         if (!(span / run->ephemeris_dt < 2.0e8)) return RB_ERR_INVALID_ARG;

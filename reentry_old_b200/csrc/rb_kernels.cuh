@@ -938,6 +938,8 @@ struct AdaptiveParams {
     double *impact_time;   // [n] NaN = none
     uint8_t *status;       // [n] rb_traj_status
     int32_t *n_samples, *n_accepted, *n_rejected;
+    double *step_log;      // [step_capacity][7][n]: (t_old, y_old) of every accepted step, or nullptr
+    int64_t step_capacity;
     // ephemeris grid (optional): hot entries at t = eph_t0 + k / eph_inv_dt, k = 0 .. eph_n - 1
     const double *eph;
     double eph_t0, eph_inv_dt;
@@ -1170,6 +1172,11 @@ __global__ void __launch_bounds__(ADAPTIVE_BLOCK, 6) k_adaptive(const AdaptivePa
             ++rej;
         }
         if (failed) { if (status == RB_TRAJ_ALIVE) status = RB_TRAJ_STEP_FAILED; break; }
+        if (acc < p.step_capacity) {   // progress_event's "root" and state of this step: its start
+            double *sl = p.step_log + ((int64_t)acc * 7) * p.n + tid;
+            sl[0] = t;
+            for (int c = 0; c < 6; ++c) sl[(c + 1) * p.n] = y[c];
+        }
         ++acc;
         typename std::conditional<DOP, DenseDop, Dense>::type d;
         if constexpr (DOP) {   // _dense_output_impl: stages 13..15, then F

@@ -577,13 +577,16 @@ class SpacecraftModel:
 
     # ------------------------------------------------------------ adaptive mode (N4)
     def run_ensemble_adaptive(self, y0, t_span, t_eval_dt, n_eval=None, rtol=1e-8, atol=1e-10, Cd=None, A=None, m=None,
-                              store_samples=True, max_steps=1_000_000, event_altitude=1000.0, ephemeris_dt=0.0) -> EnsembleResult:
+                              store_samples=True, max_steps=1_000_000, event_altitude=1000.0, ephemeris_dt=0.0,
+                              step_log_capacity=0) -> EnsembleResult:
         """The reference's integrator as shipped (solve_ivp RK45, rtol 1e-8, atol 1e-10, spacecraft_model.py:516)
         for N independent initial states, each on its own adaptive time axis.  Samples are the dense-output
         values at t_span[0] + k * t_eval_dt (k < n_eval; default: np.arange(t0, tf, dt), app.py:171) that
         are not after the terminal altitude event.  ephemeris_dt > 0 takes Sun / Moon / solar factor from a grid of that
         spacing (device-built, 4-point Lagrange; 16 s changes positions by < 1e-10 m) instead of evaluating the
-        reference's ephemeris functions at every stage time of every trajectory."""
+        reference's ephemeris functions at every stage time of every trajectory.  step_log_capacity > 0 also returns
+        `res.step_log` [capacity, 7, n]: start time and state of every accepted step (what solve_ivp reports as the roots of
+        run_simulation's always-zero progress_event, spacecraft_model.py:505-511)."""
         torch = _torch()
         ctx = self._ctx()
         if self.sim_type not in ("RK45", "RK23", "DOP853"):
@@ -605,6 +608,8 @@ class SpacecraftModel:
         n_samples = torch.empty(n, dtype=torch.int32, device=dev)
         n_acc = torch.empty(n, dtype=torch.int32, device=dev)
         n_rej = torch.empty(n, dtype=torch.int32, device=dev)
+        step_log = torch.full((int(step_log_capacity), 7, n), float("nan"), dtype=torch.float64, device=dev) \
+            if step_log_capacity > 0 else None
         arr = [None if a is None else self._dev(a, n) for a in (Cd, A, m)]
         rin = L.RbIn(n=n, y0=y0.data_ptr(), y0_traj_stride=y0.stride(0), y0_comp_stride=y0.stride(1),
                      cd=None if arr[0] is None else arr[0].data_ptr(), area=None if arr[1] is None else arr[1].data_ptr(),
@@ -617,7 +622,8 @@ class SpacecraftModel:
         out = L.RbAdaptiveOut(samples=None if samples is None else samples.data_ptr(), sample_stride=L.RB_SAMPLE_FIELDS * n,
                               field_stride=n, final_state=final_state.data_ptr(), impact_time=impact_time.data_ptr(),
                               status=status.data_ptr(), n_samples=n_samples.data_ptr(), n_accepted=n_acc.data_ptr(),
-                              n_rejected=n_rej.data_ptr())
+                              n_rejected=n_rej.data_ptr(), step_log=None if step_log is None else step_log.data_ptr(),
+                              step_capacity=int(step_log_capacity) if step_log is not None else 0)
         stream = torch.cuda.current_stream(ctx.device).cuda_stream
         if n > 0:
             ctx.check(ctx.lib.rb_propagate_adaptive(ctx.handle, C.byref(rin), C.byref(run), C.byref(out), stream),
@@ -628,6 +634,7 @@ class SpacecraftModel:
                              stats=dict(kernel_launches=1, propagate_launches=1, steps_enqueued=0, last_polled_live=-1,
                                         propagate_ms=0.0))
         res.n_accepted, res.n_rejected = n_acc, n_rej
+        res.step_log = step_log
         return res
 
     # ------------------------------------------------------------------ run_simulation
@@ -700,7 +707,8 @@ class SpacecraftModel:
             spacing = max(tf - t0, 1.0)
         if abs(t_eval[0] - t0) > 1e-9 * max(1.0, abs(t0)):
             raise ValueError("t_eval must start at t_span[0]")
-        res = self.run_ensemble_adaptive(np.asarray(y0, dtype=np.float64).reshape(1, 6), (t0, tf), spacing, n_eval=t_eval.size)
+        res = self.run_ensemble_adaptive(np.asarray(y0, dtype=np.float64).reshape(1, 6), (t0, tf), spacing, n_eval=t_eval.size,
+                                         step_log_capacity=1 << 17)
         n_valid = int(res.n_samples[0].item())
         samples = res.samples[:n_valid, :, 0].cpu().numpy()
         status = int(res.status[0].item())
@@ -708,8 +716,15 @@ class SpacecraftModel:
         sol = OdeResultLike()
         sol.t = t_eval[:n_valid].copy()
         sol.y = np.ascontiguousarray(samples[:, :6].T)
-        sol.t_events = [np.array([float(res.impact_time[0].item())]) if hit else np.array([]), np.array([])]
-        sol.y_events = [res.final_state[:, 0].cpu().numpy()[None, :] if hit else np.empty((0, 6)), np.empty((0, 6))]
+        # progress_event (spacecraft_model.py:505-511) is identically zero: solve_ivp reports the START of every accepted step
+        # as its root (ivp.py:677-699, brentq returns the bracket's left end when f is zero there)
+        n_log = min(int(res.n_accepted[0].item()), res.step_log.shape[0])
+        log = res.step_log[:n_log, :, 0].cpu().numpy()
+        sol.t_events = [np.array([float(res.impact_time[0].item())]) if hit else np.array([]), log[:, 0].copy()]
+        sol.y_events = [res.final_state[:, 0].cpu().numpy()[None, :] if hit else np.empty((0, 6)), log[:, 1:].copy()]
+        if progress_callback is not None and tf > t0:
+            for ts in log[:, 0]:   # the reference reports progress from inside progress_event, once per step
+                progress_callback((ts - t0) / (tf - t0), time.time() - self.start_time)
         sol.status = 1 if hit else (0 if status == L.TRAJ_ALIVE else -1)
         sol.success = status in (L.TRAJ_ALIVE, L.TRAJ_IMPACTED)
         sol.message = ("A termination event occurred." if hit else

@@ -156,6 +156,20 @@ def test_device_adaptive_vs_reference(oracle, golden_dir):
         check(k, c, sol.t, sol.y, te, sol.nfev, None, exact_counts=False)
         assert sol.status == c["status"]
         assert np.allclose(sol.additional_data["altitude"], c["altitude"], rtol=0, atol=1e-2)
+        # t_events[1] / y_events[1]: the roots of the always-zero progress_event = the start of every accepted step
+        # (golden steps_t = the accepted step times of the same solve_ivp call; the reference's t_events[1] is steps_t[:-1])
+        steps = np.load(os.path.join(golden_dir, "adaptive.npz"))[f"steps_t_{k}"][:-1]
+        assert sol.y_events[1].shape == (len(sol.t_events[1]), 6) and np.array_equal(sol.y_events[1][0], c["y0"])
+        assert sol.t_events[1][0] == 0.0 and np.all(np.diff(sol.t_events[1]) > 0)
+        # same opening steps; later ones may shift where an accept / reject decision flips (see check)
+        # (step sizes are 0.9 h err^(-1/5) of an error norm that is itself a ~1e8 cancellation: 1e-8 of RHS rounding
+        # moves them by 1e-6 .. 1e-5 relative within a few steps, more in the steep entry)
+        assert np.allclose(sol.t_events[1][:4], steps[:4], rtol=1e-6, atol=1e-12), (k, sol.t_events[1][:4], steps[:4])
+        assert np.allclose(sol.t_events[1][:12], steps[:12], rtol=1e-4, atol=1e-12), (k, sol.t_events[1][:12], steps[:12])
+        assert abs(len(sol.t_events[1]) - len(steps)) <= 0.05 * len(steps), (k, len(sol.t_events[1]), len(steps))
+    calls = []
+    m.run_simulation((0, c["tf"]), c["y0"], np.arange(0, c["tf"], c["dt"]), progress_callback=lambda p, el: calls.append(p))
+    assert len(calls) == len(sol.t_events[1]) + 1 and calls[0] == 0.0 and all(0.0 <= p <= 1.0 for p in calls)
     # ensemble form: many trajectories, each on its own time axis, equals the single-trajectory runs
     k, c = next(cases(golden_dir))
     m = SpacecraftModel(Cd=c["Cd"], A=c["A"], m=c["m"], epoch=c["epoch"], gmst0=c["gmst0"])

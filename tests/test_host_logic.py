@@ -55,7 +55,7 @@ def test_abi_exports_every_declared_symbol(product_lib):
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
     for name in declared:
         assert hasattr(product_lib, name), name
-    assert product_lib.rb_abi_version() == 2
+    assert product_lib.rb_abi_version() == L.RB_ABI_VERSION == 3
     assert product_lib.rb_strerror(0) == b"ok" and b"invalid" in product_lib.rb_strerror(-1)
     assert product_lib.rb_time_table_entries(100) == 501
 
