@@ -537,9 +537,13 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        by_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(by_rank, t)
+        ms_by_rank = [float(x[0]) / K for x in by_rank]
         ms, total_steps_pass = float(tmax[0]), float(tsum[1])
     else:
         total_steps_pass = float(steps_per_pass)
+        ms_by_rank = [ms / K]
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = total_steps_pass * K / (ms * 1e-3)
 
@@ -639,7 +643,10 @@ def main():
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config_dict(w, world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_per_pass * K), "roofline": roofline, "cpu_baseline": cpu,
-                "traj_steps_per_pass": total_steps_pass, "parity": parity, "e2e_c5": c5}
+                "traj_steps_per_pass": total_steps_pass, "parity": parity, "e2e_c5": c5,
+                "ms_per_step_by_rank": ms_by_rank,
+                "ms_per_step_note": "device time (CUDA events) of each rank's K timed passes / K; ms_per_step is their maximum; at "
+                                    "N > 1 a pass includes the NCCL gather of the [n, 10] summaries to rank 0"}
         emit(line)
     if world > 1:
         dist.barrier()
