@@ -502,7 +502,7 @@ def main():
     def one_step(profile=False):
         r = model.run_ensemble(y0, t0=0.0, dt=w.dt, n_steps=w.n_steps, out_stride=w.out_stride,
                                steps_per_launch=w.steps_per_launch, profile=profile, samples="packed", packed_capacity=pack_cap)
-        g = gather_summaries(r, dst=0) if world > 1 else None
+        g = gather_summaries(r, dst=0, counts=[n] * world) if world > 1 else None   # (known shard sizes: no count exchange)
         return r, g
 
     def barrier():

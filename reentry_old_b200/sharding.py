@@ -26,17 +26,24 @@ def pack_summary(final_state, impact_time, impact_step, status, n_samples):
     return out
 
 
-def gather_packed(packed, dst=0, group=None):
+def gather_packed(packed, dst=0, group=None, counts=None):
     """One collective: gather variable-length [n_r, 10] shards to rank `dst` in rank order.
-    Returns the concatenated [sum n_r, 10] tensor on dst, None elsewhere."""
+    Returns the concatenated [sum n_r, 10] tensor on dst, None elsewhere.
+    counts: the shard sizes of all ranks when the caller knows them (shard_range gives them): without it they are
+    exchanged first, which costs a small all_gather and a host synchronisation per call."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    counts = [torch.zeros(1, dtype=torch.int64, device=packed.device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([packed.shape[0]], dtype=torch.int64, device=packed.device), group=group)
-    counts = [int(c.item()) for c in counts]
+    if counts is None:
+        counts = [torch.zeros(1, dtype=torch.int64, device=packed.device) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([packed.shape[0]], dtype=torch.int64, device=packed.device), group=group)
+        counts = [int(c.item()) for c in counts]
+    else:
+        counts = [int(c) for c in counts]
+        if len(counts) != world or counts[rank] != packed.shape[0]:
+            raise ValueError(f"counts {counts} do not describe this gather (rank {rank} holds {packed.shape[0]} rows)")
     nmax = max(counts)
     buf = packed
     if packed.shape[0] != nmax:  # pad so that every rank contributes the same shape
@@ -50,10 +57,10 @@ def gather_packed(packed, dst=0, group=None):
     return None
 
 
-def gather_summaries(result, dst=0, group=None):
+def gather_summaries(result, dst=0, group=None, counts=None):
     """EnsembleResult of this rank's shard -> [N_total, 10] on rank dst (None elsewhere)."""
     return gather_packed(pack_summary(result.final_state, result.impact_time, result.impact_step, result.status,
-                                      result.n_samples), dst=dst, group=group)
+                                      result.n_samples), dst=dst, group=group, counts=counts)
 
 
 def unpack_summary(packed):
@@ -72,4 +79,5 @@ def run_sharded(model, workload_fn, n_total, group=None, **run_kw):
     lo, hi = shard_range(n_total, rank, world)
     y0, kw = workload_fn(lo, hi)
     res = model.run_ensemble(y0, **kw, **run_kw)
-    return res, gather_summaries(res, dst=0, group=group)
+    counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    return res, gather_summaries(res, dst=0, group=group, counts=counts)

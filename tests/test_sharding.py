@@ -36,10 +36,19 @@ def _worker(rank, world, port, n_total, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = shard_range(n_total, rank, world)
     out = gather_packed(fake_shard(lo, hi), dst=0)
+    # the same gather with the shard sizes given by the caller (no count exchange, no host synchronisation)
+    counts = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    out2 = gather_packed(fake_shard(lo, hi), dst=0, counts=counts)
+    try:
+        gather_packed(fake_shard(lo, hi), dst=0, counts=[c + 1 for c in counts])
+        raise AssertionError("wrong counts accepted")
+    except ValueError:
+        pass
     if rank == 0:
+        assert torch.equal(out, out2)
         q.put(out.numpy())
     else:
-        assert out is None
+        assert out is None and out2 is None
     dist.barrier()
     dist.destroy_process_group()
 
