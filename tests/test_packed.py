@@ -174,3 +174,24 @@ def test_blocks_that_start_fully_retired(Model, torch):
         torch.cuda.synchronize()
         assert torch.equal(r.impact_step, base.impact_step) and torch.equal(r.final_state, base.final_state)
         assert _same(torch, r.samples, base.samples)
+
+
+@pytest.mark.parametrize("n", [1, 15, 17, 129, 1025])
+def test_packed_ragged_sizes(Model, torch, n):
+    """Ensemble sizes that are not a multiple of the slab-width granule (16), of a warp or of a block -- one trajectory
+    included: packed == dense on the device path and on the host-buffer path."""
+    n_steps, stride = 2048, 5
+    m, y0 = _ensemble(Model, n, 5)
+    dense = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=stride)
+    pk = m.run_ensemble(y0, dt=0.5, n_steps=n_steps, out_stride=stride, samples="packed")
+    assert _same(torch, pk.packed.to_dense(), dense.samples)
+    assert torch.equal(pk.impact_step, dense.impact_step) and torch.equal(pk.n_samples, dense.n_samples)
+    for i in {0, n // 2, n - 1}:
+        tr = pk.packed.trajectory(i)
+        ns = int(dense.n_samples[i])
+        assert tr.shape == (ns, 8) and torch.equal(tr, dense.samples[:ns, :, i])
+    bufs = m.host_buffers(n, n_steps, stride, packed_capacity=8 * (n + 16) * (n_steps // stride + 2))
+    bufs["y0"].copy_(y0)
+    r = m.run_ensemble_host(bufs, dt=0.5)
+    assert torch.equal(r.impact_step, dense.impact_step.cpu()) and torch.equal(r.final_state, dense.final_state.cpu())
+    assert _same(torch, r.packed.to_dense(n_out=n_steps // stride + 1), dense.samples.cpu())
