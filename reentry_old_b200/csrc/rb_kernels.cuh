@@ -1275,6 +1275,14 @@ __global__ void k_math_probe(int op, int64_t n, const double *x, const double *y
         case 5: r = rb_pow_near1(a, b); break;
         case 6: r = rb_log1p_small(a); break;
         case 7: r = rb_exp_bounded(b * rb_log1p_small(a)); break;   // the pressure law as density() evaluates it
+        // the budgeted variants of the hot RHS (FAST), each with its own stated bound
+        case 8: r = rb_exp_bounded<TabGlobal, true>(a); break;
+        case 9: r = rb_log1p_small<true>(a); break;
+        case 10: r = rb_sqrt_q(a); break;
+        case 11: r = third_body_k3(b, a); break;
+        case 12: r = rb_rsqrt_q(a); break;
+        case 13: r = rb_rcp_q(a); break;
+        case 14: r = rb_atan2_unit<true>(a, b); break;
         default: r = nan("");
     }
     out[i] = r;

@@ -46,10 +46,10 @@ RB_HD void hot_entry(const double *__restrict__ e, double *__restrict__ h) {
 // (ptxas rematerialises them); constant-bank operands (c[3][off]) ride along with DFMA/DMUL
 // for free.  The host copy serves the CPU build of this header (tests/host_harness.cu).
 struct Consts {
-    double omega, neg_mu, j2f, j2c, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc, latc_rad;
+    double omega, neg_mu, j2c, j2c2, moon_k, sun_k, earth_r, one_m_e2, e2r, one_m_e2r_over_r, tan_tol, tan_tol_sure, rad2deg, latc, latc_rad;
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double sig_c, top_c;         // sig_ks sig_x0 ; -top_k top_h  (the exponents as one fma of the altitude)
-    double sea_rho;
+    double sea_rho, j2f;         // (j2f: diagnostics only -- kept off the 16-byte pairs of the hot constants above)
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
     double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
@@ -85,15 +85,15 @@ static_assert(rb_hi_word_(90000.0) == 0x40F5F900 && rb_hi_word_(1.0) == 0x3FF000
                       rb_gr_(i) == 0.0 ? rb_isok_(i) : rb_powk_(i), rb_bpz_(i) / RB_R_GAS, 0.0, 0.0}
 
 #define RB_CONSTS_INIT                                                                              \
-    {RB_EARTH_OMEGA, -RB_EARTH_MU, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),      \
-     1.5 * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),                                                 \
+    {RB_EARTH_OMEGA, -RB_EARTH_MU,                                                                   \
+     1.5 * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R), 3.0 * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),    \
      RB_MOON_K, RB_SUN_K, RB_EARTH_R, 1.0 - RB_EARTH_E2, RB_EARTH_E2 * RB_EARTH_R,                         \
      (1.0 - RB_EARTH_E2 * RB_EARTH_R) / RB_EARTH_R, 1.0000000000003333e-06 /* tan(1e-6) */, 100.0 * 1.0000000000003333e-06, 180.0 / RB_PI,           \
      RB_LAT_FACTOR_COEF / 90.0, (RB_LAT_FACTOR_COEF / 90.0) * (180.0 / RB_PI), RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS, RB_SIGMOID_X0,                 \
      RB_SOLAR_BLEND_ALT, rb_bpz_(7) / (RB_R_GAS * rb_bt_(7)), RB_R_GAS, rb_bp_(7), rb_bt_(7), rb_bpz_(7),                            \
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
      (RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS) * RB_SIGMOID_X0, -(rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT) * rb_bp_(7),   \
-     RB_SEA_LEVEL_RHO,                                                                               \
+     RB_SEA_LEVEL_RHO, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),                   \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
      RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_), RB_L8_(rb_bphi_)}
 
@@ -259,7 +259,9 @@ RB_HD double haversine(double lat1, double lon1, double lat2, double lon2) {
 // (spacecraft_model.py:181-188, :71-99, :148-168, :110-127).  solar_time = time-only part of the
 // solar factor from the time table.  The two exponentials of the top layer (:84 and :89) are
 // one exp of the summed exponent.
-template <class TB = TabGlobal>
+// FAST (the hot RHS): 1/T and the sigmoid's reciprocal by the second-order form (<= 3.3e-12 relative of a factor of rho), the
+// truncated exp / log1p of rb_math.cuh (2e-15): three + three FP64 instructions less per evaluation.
+template <bool FAST = false, class TB = TabGlobal>
 RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out, const TB &tb = TB()) {
     // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
     // solar_m1 = solar_time - 1 (both from the time table)
@@ -308,16 +310,35 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         T = fma(L, dh, lay[2]);
         const double k = lay[4];
         arg = dh * k;                                                   // isothermal: P_i e^(k dh), :84
-        if (L != 0.0) arg = k * rb_log1p_small(lay[3] * dh);            // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
-        c0 = lay[5] * rb_rcp(T);                                        // P / (R_GAS T), :88
+        if (L != 0.0) arg = k * rb_log1p_small<FAST>(lay[3] * dh);      // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
+        c0 = lay[5] * (FAST ? rb_rcp_q(T) : rb_rcp(T));                 // P / (R_GAS T), :88
     }
     T_out = T;
     if (blend)   // (the sigmoid's exponent lies in [-2.6, 0.8] for 0 < altitude < 90 km: no clamp)
-        factor = fma(solar_m1, rb_rcp(1.0 + rb_exp_bounded(fma(-KC(sig_ks), altitude, KC(sig_c)), tb)), 1.0);   // 1 + (f - 1) / (1 + e^(-k (x - x0)))
+    {   // 1 + (f - 1) / (1 + e^(-k (x - x0)))
+        const double sg = 1.0 + rb_exp_bounded<TB, FAST>(fma(-KC(sig_ks), altitude, KC(sig_c)), tb);
+        factor = fma(solar_m1, FAST ? rb_rcp_q(sg) : rb_rcp(sg), 1.0);
+    }
     // (evaluating the two exponentials interleaved, to load their coefficients once, measured no gain: 10.14 vs 10.15 G)
-    const double ex = rb_exp_bounded(arg, tb);
+    const double ex = rb_exp_bounded<TB, FAST>(arg, tb);
     return (c0 * ex) * (latitude_factor * factor);
 #undef RB_ALT_GE
+}
+// k / |d|^3 from d2 = |d|^2 for the direct third-body terms of the hot RHS: with the MUFU seed y and e = 1 - d2 y^2,
+// |d|^-3 = y^3 (1 - e)^(-3/2) = y^3 (1 + 1.5 e + 1.875 e^2 ..): the first-order form has relative error 1.9 e^2 <= 6e-12 of
+// accelerations of 1e-6 m/s^2 -- six FP64 instructions instead of the seven of a second-order rsqrt followed by the cube.
+RB_HD double third_body_k3(double k, double d2) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d2));
+    const double y2 = y * y;
+    const double e = fma(-d2, y2, 1.0);
+    const double y3k = (k * y) * y2;
+    return fma(y3k, e * 1.5, y3k);
+#else
+    const double id = 1.0 / sqrt(d2);
+    return k * (id * id * id);
+#endif
 }
 // bcp: where the body constant bc = Cd A / (2 m) is read from AT ITS USE (the very end of the evaluation): the step
 // kernel parks it in shared memory instead of holding two registers through the whole evaluation.
@@ -336,7 +357,9 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     // point-mass gravity, :451 : -mu r / |r|^3, and J2, :377-388 : f = 1.5 mu J2 R^2 / r^5 ;
     // a = f r (5 z^2/r^2 - {1,1,3}).  Both are (scalar) * r: the scalars are summed first.
     const double gk = KC(neg_mu) * ir3;
-    const double q = (5.0 * ir2) * (z * z);
+    const double zr2 = ir2 * (z * z);
+    const double q = 5.0 * zr2;                       // (DIAG form)
+    const double omq = fma(-5.0, zr2, 1.0);           // 1 - q
     double ax, ay, az;
     if (DIAG) {   // the two terms separately, as the reference reports them
         const double f = KC(j2f) * (ir3 * ir2);
@@ -346,9 +369,10 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         ax = diag->a_grav[0] + diag->a_j2[0]; ay = diag->a_grav[1] + diag->a_j2[1]; az = diag->a_grav[2] + diag->a_j2[2];
     } else {
         // f = -gk j with j = 1.5 J2 R^2 / r^2:  k_xy = gk (1 + j (1 - q)),  k_z = k_xy + 2 gk j   (q = 5 z^2 / r^2)
-        const double gj = gk * (KC(j2c) * ir2);
-        const double kxy = fma(gj, 1.0 - q, gk);
-        const double kz = fma(gj, 2.0, kxy);
+        //   = gk + j2c (gk/r^2)(1 - q),  k_z = k_xy + 2 j2c (gk/r^2): one multiply less than forming gj first
+        const double gku = gk * ir2;
+        const double kxy = fma(KC(j2c), gku * omq, gk);
+        const double kz = fma(KC(j2c2), gku, kxy);
         ax = fma(kxy, x, e[H_NIND + 0]); ay = fma(kxy, y, e[H_NIND + 1]); az = fma(kz, z, e[H_NIND + 2]);
     }
     // third bodies as a lambda: evaluated inside the drag block (fills the latency of its serial tail)
@@ -375,14 +399,12 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         } else {   // the indirect terms are already in (ax, ay, az): accumulate the direct ones
             {
                 const double dx = e[H_MOON + 0] - x, dy = e[H_MOON + 1] - y, dz = e[H_MOON + 2] - z;
-                const double id = rb_rsqrt_q(fma(dz, dz, fma(dx, dx, dy * dy)));
-                const double k3 = KC(moon_k) * (id * id * id);
+                const double k3 = third_body_k3(KC(moon_k), fma(dz, dz, fma(dx, dx, dy * dy)));
                 ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
             }
             {
                 const double dx = e[H_SUN + 0] - x, dy = e[H_SUN + 1] - y, dz = e[H_SUN + 2] - z;
-                const double id = rb_rsqrt_q(fma(dz, dz, fma(dx, dx, dy * dy)));
-                const double k3 = KC(sun_k) * (id * id * id);
+                const double k3 = third_body_k3(KC(sun_k), fma(dz, dz, fma(dx, dx, dy * dy)));
                 ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
             }
         }
@@ -400,12 +422,14 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         double T, rho, lat_deg = 0.0;
         if (DIAG) {
             lat_deg = pair_abs_latitude_deg(gA, gB);
-            rho = density(altitude, fma(KC(latc), lat_deg, 1.0), e[E_SOLAR], e[E_SOLAR] - 1.0, T, tb);
+            rho = density<false>(altitude, fma(KC(latc), lat_deg, 1.0), e[E_SOLAR], e[E_SOLAR] - 1.0, T, tb);
         } else {   // radians straight into the latitude factor (the degree conversion folds into the coefficient)
-            rho = density(altitude, fma(KC(latc_rad), pair_abs_latitude_rad<true>(gA, gB, tb), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T, tb);
+            rho = density<true>(altitude, fma(KC(latc_rad), pair_abs_latitude_rad<true>(gA, gB, tb), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T, tb);
         }
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
-        const double vn = w2 * rb_rsqrt(w2);
+        // (hot RHS: |v_rel| by one Newton step, 1.3e-12 relative -- of a drag acceleration below 100 m/s^2: 1.3e-10 m/s^2,
+        // 1e-14 of the position over a reentry; the parity bar is 1e-9)
+        const double vn = FAST ? rb_sqrt_q(w2) : w2 * rb_rsqrt(w2);
         const double kd = -(rho * *bcp) * vn;
         if (DIAG) {
             const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;

@@ -459,10 +459,23 @@ def test_math_primitives(torch):
     z = x - 1.0                                                        # T/T_i - 1 = (L/T_i) dh, as density() forms it
     assert np.max(np.abs(run(6, z) - np.log1p(z))) <= 1.2e-16
     assert np.max(np.abs(run(7, z, k) / np.power(1.0 + z, k) - 1.0)) <= 1e-14   # k <= 34: exponent error k ulp(log)
+    # the budgeted variants of the hot RHS (FAST paths of rb_math.cuh / rb_physics.cuh), each against its stated bound
+    x = rng.uniform(-3.3, 0.9, n)                                      # exponents of the density's two exponentials
+    assert np.max(np.abs(run(8, x) / np.exp(x) - 1.0)) <= 3e-15        # r^6/720 dropped: 2.2e-15
+    assert np.max(np.abs(run(9, z) / np.log1p(np.where(z == 0, 1e-300, z)) - 1.0)) <= 2.5e-15   # u^8/17 dropped: 1.6e-15
+    x = 10 ** rng.uniform(-4, 16, n)                                   # |v_rel|^2, T, 1 + e^s, |d|^2
+    # one Newton step on the MUFU seed (relative error e/2 <= 9e-7): 3/8 e^2 for sqrt / rsqrt, e^2 for rcp, 15/8 e^2 for x^-1.5
+    errs = dict(sqrt_q=np.max(np.abs(run(10, x) / np.sqrt(x) - 1.0)), rsqrt_q=np.max(np.abs(run(12, x) * np.sqrt(x) - 1.0)),
+                rcp_q=np.max(np.abs(run(13, x) * x - 1.0)))
+    kk = rng.uniform(1e12, 2e20, n)
+    errs["k3"] = np.max(np.abs(run(11, x, kk) / (kk * x ** -1.5) - 1.0))
+    print("second-order forms, max relative error:", errs)
+    assert errs["sqrt_q"] <= 2e-12 and errs["rsqrt_q"] <= 2e-12 and errs["rcp_q"] <= 5e-12 and errs["k3"] <= 1e-11, errs
     th = np.concatenate([rng.uniform(0, np.pi / 2, n - 5), [0.0, np.pi / 2, np.pi / 4, 1e-9, np.pi / 2 - 1e-9]])
     s, c = np.sin(th), np.cos(th)
     nrm = np.hypot(s, c); s, c = s / nrm, c / nrm
     assert np.max(np.abs(run(4, s, c) - np.arctan2(s, c))) <= 4.5e-16
+    assert np.max(np.abs(run(14, s, c) - np.arctan2(s, c))) <= 1.5e-13   # hot-RHS variant: u^3/7 dropped (6e-14), rcp by one Newton step
 
 
 def test_fp64_peak_probe(torch):
