@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(ADAPTIVE_BLOCK, 6) k_adaptive(const AdaptivePa
             hot_entry(ent, hot);
         }
         double a[3];
-        acceleration<false>(hot, yy, yy + 3, body, a, nullptr);
+        acceleration<false, false, false>(hot, yy, yy + 3, body, a, nullptr);   // (full-precision arithmetic, see rb_physics.cuh)
         dy[0] = yy[3]; dy[1] = yy[4]; dy[2] = yy[5]; dy[3] = a[0]; dy[4] = a[1]; dy[5] = a[2];
     };
 #pragma unroll

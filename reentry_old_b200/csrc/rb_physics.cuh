@@ -122,13 +122,16 @@ struct Body {  // per-trajectory constant bc = 0.5 Cd A / m (SpacecraftModel.Cd 
     double bc;
 };
 struct RhsOut;
-template <bool DIAG, bool SKIP = false, class TB = TabGlobal>
+// FAST: the budgeted arithmetic of the fixed-step hot path (second-order sqrt / rcp / rsqrt, truncated series tails; every
+// variant's bound is stated at its definition and pinned by rb_math_probe): default for the non-diagnostic evaluation.  The
+// adaptive kernel evaluates the same table-entry form with FAST = false (its error estimator sees the RHS at full precision).
+template <bool DIAG, bool SKIP = false, class TB = TabGlobal, bool FAST = !DIAG>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const double *bcp,
                         double a[3], RhsOut *diag, double *altitude_out = nullptr, const TB &tb = TB());
-template <bool DIAG, bool SKIP = false>
+template <bool DIAG, bool SKIP = false, bool FAST = !DIAG>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const Body &b,
                         double a[3], RhsOut *diag, double *altitude_out = nullptr) {
-    acceleration<DIAG, SKIP, TabGlobal>(e, r, v, &b.bc, a, diag, altitude_out, TabGlobal());
+    acceleration<DIAG, SKIP, TabGlobal, FAST>(e, r, v, &b.bc, a, diag, altitude_out, TabGlobal());
 }
 RB_HD Body make_body(double cd, double area, double mass) { return Body{0.5 * cd * area / mass}; }
 
@@ -259,8 +262,8 @@ RB_HD double haversine(double lat1, double lon1, double lat2, double lon2) {
 // (spacecraft_model.py:181-188, :71-99, :148-168, :110-127).  solar_time = time-only part of the
 // solar factor from the time table.  The two exponentials of the top layer (:84 and :89) are
 // one exp of the summed exponent.
-// FAST (the hot RHS): 1/T and the sigmoid's reciprocal by the second-order form (<= 3.3e-12 relative of a factor of rho), the
-// truncated exp / log1p of rb_math.cuh (2e-15): three + three FP64 instructions less per evaluation.
+// FAST (the hot RHS): the truncated exp / log1p tails of rb_math.cuh (<= 2.2e-15 relative): four FP64 instructions less per
+// evaluation.  Everything that multiplies into the drag term keeps full-precision reciprocals and roots.
 template <bool FAST = false, class TB = TabGlobal>
 RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out, const TB &tb = TB()) {
     // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
@@ -311,13 +314,13 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         const double k = lay[4];
         arg = dh * k;                                                   // isothermal: P_i e^(k dh), :84
         if (L != 0.0) arg = k * rb_log1p_small<FAST>(lay[3] * dh);      // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
-        c0 = lay[5] * (FAST ? rb_rcp_q(T) : rb_rcp(T));                 // P / (R_GAS T), :88
+        c0 = lay[5] * rb_rcp(T);                                        // P / (R_GAS T), :88
     }
     T_out = T;
     if (blend)   // (the sigmoid's exponent lies in [-2.6, 0.8] for 0 < altitude < 90 km: no clamp)
     {   // 1 + (f - 1) / (1 + e^(-k (x - x0)))
         const double sg = 1.0 + rb_exp_bounded<TB, FAST>(fma(-KC(sig_ks), altitude, KC(sig_c)), tb);
-        factor = fma(solar_m1, FAST ? rb_rcp_q(sg) : rb_rcp(sg), 1.0);
+        factor = fma(solar_m1, rb_rcp(sg), 1.0);
     }
     // (evaluating the two exponentials interleaved, to load their coefficients once, measured no gain: 10.14 vs 10.15 G)
     const double ex = rb_exp_bounded<TB, FAST>(arg, tb);
@@ -342,10 +345,9 @@ RB_HD double third_body_k3(double k, double d2) {
 }
 // bcp: where the body constant bc = Cd A / (2 m) is read from AT ITS USE (the very end of the evaluation): the step
 // kernel parks it in shared memory instead of holding two registers through the whole evaluation.
-template <bool DIAG, bool SKIP, class TB>
+template <bool DIAG, bool SKIP, class TB, bool FAST>
 RB_HD void acceleration(const double *__restrict__ e, const double r[3], const double v[3], const double *bcp,
                         double a[3], RhsOut *diag, double *altitude_out, const TB &tb) {
-    constexpr bool FAST = !DIAG;   // second-order rsqrt / rcp where only the latitude factor or a third-body term is fed
     const double x = r[0], y = r[1], z = r[2];
     const double p2 = fma(x, x, y * y);
     const double r2 = fma(z, z, p2);
@@ -399,12 +401,16 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         } else {   // the indirect terms are already in (ax, ay, az): accumulate the direct ones
             {
                 const double dx = e[H_MOON + 0] - x, dy = e[H_MOON + 1] - y, dz = e[H_MOON + 2] - z;
-                const double k3 = third_body_k3(KC(moon_k), fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double d2 = fma(dz, dz, fma(dx, dx, dy * dy));
+                const double id = FAST ? 0.0 : rb_rsqrt(d2);
+                const double k3 = FAST ? third_body_k3(KC(moon_k), d2) : KC(moon_k) * (id * id * id);
                 ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
             }
             {
                 const double dx = e[H_SUN + 0] - x, dy = e[H_SUN + 1] - y, dz = e[H_SUN + 2] - z;
-                const double k3 = third_body_k3(KC(sun_k), fma(dz, dz, fma(dx, dx, dy * dy)));
+                const double d2 = fma(dz, dz, fma(dx, dx, dy * dy));
+                const double id = FAST ? 0.0 : rb_rsqrt(d2);
+                const double k3 = FAST ? third_body_k3(KC(sun_k), d2) : KC(sun_k) * (id * id * id);
                 ax = fma(k3, dx, ax); ay = fma(k3, dy, ay); az = fma(k3, dz, az);
             }
         }
@@ -424,12 +430,14 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
             lat_deg = pair_abs_latitude_deg(gA, gB);
             rho = density<false>(altitude, fma(KC(latc), lat_deg, 1.0), e[E_SOLAR], e[E_SOLAR] - 1.0, T, tb);
         } else {   // radians straight into the latitude factor (the degree conversion folds into the coefficient)
-            rho = density<true>(altitude, fma(KC(latc_rad), pair_abs_latitude_rad<true>(gA, gB, tb), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T, tb);
+            rho = density<FAST>(altitude, fma(KC(latc_rad), pair_abs_latitude_rad<FAST>(gA, gB, tb), 1.0), e[H_SOLAR], e[H_SOLAR_M1], T, tb);
         }
         const double w2 = fma(wz, wz, fma(wx, wx, wy * wy));
-        // (hot RHS: |v_rel| by one Newton step, 1.3e-12 relative -- of a drag acceleration below 100 m/s^2: 1.3e-10 m/s^2,
-        // 1e-14 of the position over a reentry; the parity bar is 1e-9)
-        const double vn = FAST ? rb_sqrt_q(w2) : w2 * rb_rsqrt(w2);
+        // (|v_rel|, 1/T and the sigmoid's reciprocal keep the full forms also in the hot RHS: second-order forms -- 1e-12
+        // relative of the DRAG term -- were measured: +2 % throughput and reentry parity unchanged (1.9e-13), but on
+        // orbits whose perigee dips into the atmosphere the sensitivity of the trajectory amplifies them to 2.4e-9 where a
+        // rounding-level implementation stays at 1e-10: not taken)
+        const double vn = w2 * rb_rsqrt(w2);
         const double kd = -(rho * *bcp) * vn;
         if (DIAG) {
             const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;
