@@ -340,7 +340,7 @@ void rb_host_free(void *p);
  * arrays: op 0 rcp(x), 1 rsqrt(x), 2 exp(x), 3 log(x) for x in [0.7, 1.3], 4 atan2(x, y) for
  * x, y >= 0 on the unit circle, 5 pow(x, y) for x in [0.7, 1.3], 6 log1p(x) for |x| <= 0.3, 7 (1 + x)^y as the
  * density's pressure law forms it; the budgeted variants of the hot RHS: 8 exp(x) without its last term, 9 log1p(x)
- * without its last two, 10 sqrt(x), 12 rsqrt(x), 13 rcp(x) by one Newton step, 11 y / x^1.5 (third-body factor), 14 atan2 as 4 without its last term.
+ * without its last two, 10 sqrt(x), 12 rsqrt(x), 13 rcp(x) by one Newton step, 11 y / x^1.5 (third-body factor), 14 atan2 as 4 without its last term; 15 sqrt(x) at full precision.
  * y may be NULL for unary ops. */
 int32_t rb_math_probe(rb_ctx *ctx, int32_t op, int64_t n, const double *x, const double *y, double *out,
                       void *stream);

@@ -1211,7 +1211,7 @@ int32_t rb_impact_points(rb_ctx *ctx, int64_t n, const double *final_state, cons
 
 // ------------------------------------------------------------------ math self-test
 int32_t rb_math_probe(rb_ctx *ctx, int32_t op, int64_t n, const double *x, const double *y, double *out, void *stream) {
-    if (!ctx || n < 0 || !x || !out || op < 0 || op > 14) return RB_ERR_INVALID_ARG;
+    if (!ctx || n < 0 || !x || !out || op < 0 || op > 15) return RB_ERR_INVALID_ARG;
     if (n == 0) return RB_OK;
     CK(cudaSetDevice(ctx->device));
     k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, n, x, y, out);

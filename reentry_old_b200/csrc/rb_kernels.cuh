@@ -1283,6 +1283,7 @@ __global__ void k_math_probe(int op, int64_t n, const double *x, const double *y
         case 12: r = rb_rsqrt_q(a); break;
         case 13: r = rb_rcp_q(a); break;
         case 14: r = rb_atan2_unit<true>(a, b); break;
+        case 15: r = rb_sqrt(a); break;
         default: r = nan("");
     }
     out[i] = r;

@@ -437,7 +437,7 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
         // relative of the DRAG term -- were measured: +2 % throughput and reentry parity unchanged (1.9e-13), but on
         // orbits whose perigee dips into the atmosphere the sensitivity of the trajectory amplifies them to 2.4e-9 where a
         // rounding-level implementation stays at 1e-10: not taken)
-        const double vn = w2 * rb_rsqrt(w2);
+        const double vn = rb_sqrt(w2);
         const double kd = -(rho * *bcp) * vn;
         if (DIAG) {
             const double ddx = kd * wx, ddy = kd * wy, ddz = kd * wz;

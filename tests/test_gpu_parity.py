@@ -467,6 +467,7 @@ def test_math_primitives(torch):
     # one Newton step on the MUFU seed (relative error e/2 <= 9e-7): 3/8 e^2 for sqrt / rsqrt, e^2 for rcp, 15/8 e^2 for x^-1.5
     errs = dict(sqrt_q=np.max(np.abs(run(10, x) / np.sqrt(x) - 1.0)), rsqrt_q=np.max(np.abs(run(12, x) * np.sqrt(x) - 1.0)),
                 rcp_q=np.max(np.abs(run(13, x) * x - 1.0)))
+    assert ulps(run(15, x), np.sqrt(x)) <= 1.5                         # full-precision sqrt (|v_rel| of the drag term)
     kk = rng.uniform(1e12, 2e20, n)
     errs["k3"] = np.max(np.abs(run(11, x, kk) / (kk * x ** -1.5) - 1.0))
     print("second-order forms, max relative error:", errs)
