@@ -242,7 +242,7 @@ __device__ __noinline__ void nan_rows_at(double *column, int64_t sample_stride, 
 // (same size as 26 rows of BLOCK doubles)
 constexpr int PARK_ROWS = 8;   // per-thread doubles parked in shared memory: y_n[6], bc, g_old
 template <int BLOCK>
-constexpr size_t propagate_smem_bytes() {
+__host__ __device__ constexpr size_t propagate_smem_bytes() {
     return sizeof(double) * (TILE_BUFFERS * TILE_DOUBLES + (K_SLOTS * K_ROWS + PARK_ROWS) * BLOCK + TAB_DOUBLES) + 2 * sizeof(uint64_t);
 }
 
@@ -281,6 +281,8 @@ __device__ RB_RHS_LINKAGE double rhs_eval(uint32_t ent, uint32_t bca, uint32_t k
 
 template <int BLOCK, int MIN_BLOCKS, bool SKIP>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) k_propagate(const StepParams p) {
+    // (STATIC shared memory was tried so that table addresses would be link-time constants: ptxas then rebuilds the shared
+    // base from a special register in every stage -- S2R + LEA + MOV -- instead of holding it in one register: no gain)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
     double *Ks = tiles + TILE_BUFFERS * TILE_DOUBLES;

@@ -50,6 +50,7 @@ struct Consts {
     double sig_ks, sig_x0, blend_alt, top_rho0, rgas, top_h, top_T, top_P, top_k;
     double sig_c, top_c;         // sig_ks sig_x0 ; -top_k top_h  (the exponents as one fma of the altitude)
     double sea_rho, j2f;         // (j2f: diagnostics only -- kept off the 16-byte pairs of the hot constants above)
+    double j2c5n;                // -5 j2c
     double bp[RB_N_LAYERS], gr[RB_N_LAYERS], bt[RB_N_LAYERS], bpz[RB_N_LAYERS];
     double iso_k[RB_N_LAYERS];   // gM / (R* T_i)        (isothermal layers, spacecraft_model.py:84)
     double pow_k[RB_N_LAYERS];   // gM / (R* L_i)        (gradient layers, :86); 0 where L_i == 0
@@ -94,6 +95,7 @@ static_assert(rb_hi_word_(90000.0) == 0x40F5F900 && rb_hi_word_(1.0) == 0x3FF000
      rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT,                                                            \
      (RB_SIGMOID_K * RB_SIGMOID_SMOOTHNESS) * RB_SIGMOID_X0, -(rb_isok_(7) - 1.0 / RB_SCALE_HEIGHT) * rb_bp_(7),   \
      RB_SEA_LEVEL_RHO, 1.5 * RB_EARTH_MU * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),                   \
+     -7.5 * RB_EARTH_J2 * (RB_EARTH_R * RB_EARTH_R),                                                 \
      RB_L8_(rb_bp_), RB_L8_(rb_gr_), RB_L8_(rb_bt_), RB_L8_(rb_bpz_), RB_L8_(rb_isok_),              \
      RB_L8_(rb_powk_), RB_L8_(rb_invbt_), RB_L8_(RB_LAYER_), RB_L8_(rb_bphi_)}
 
@@ -268,9 +270,19 @@ template <bool FAST = false, class TB = TabGlobal>
 RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out, const TB &tb = TB()) {
     // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
     // solar_m1 = solar_time - 1 (both from the time table)
-    if (altitude <= 0.0) {   // at or below the sphere of the equatorial radius (never on a live reentry's hot path): the
-        T_out = RB_SEA_LEVEL_T;  // constant comes from the constant bank -- as a literal the compiler materialises it with
-        return KC(sea_rho);      // two predicated moves in front of the branch of every evaluation
+    if (altitude <= 0.0) {   // at or below the sphere of the equatorial radius (never on a live reentry's hot path)
+        T_out = RB_SEA_LEVEL_T;
+#if defined(__CUDA_ARCH__)
+        // The constant is read by a VOLATILE constant-bank load: as an ordinary literal or constant-bank value the compiler
+        // hoists its materialisation (two moves, or a uniform load and two moves) in front of the branch of every
+        // evaluation; this way ONE predicated load is issued there.
+        static_assert(offsetof(Consts, sea_rho) == 208, "update the offset in the load below");
+        double rho0;
+        asm volatile("ld.const.f64 %0, [_ZN2rb3c_kE+208];" : "=d"(rho0));
+        return rho0;
+#else
+        return KC(sea_rho);
+#endif
     }
     double factor = solar_time;
     // From here on altitude > 0 (or NaN): the thresholds (90 km, the layer breakpoints) have zero low words, so
@@ -361,7 +373,6 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     const double gk = KC(neg_mu) * ir3;
     const double zr2 = ir2 * (z * z);
     const double q = 5.0 * zr2;                       // (DIAG form)
-    const double omq = fma(-5.0, zr2, 1.0);           // 1 - q
     double ax, ay, az;
     if (DIAG) {   // the two terms separately, as the reference reports them
         const double f = KC(j2f) * (ir3 * ir2);
@@ -372,8 +383,10 @@ RB_HD void acceleration(const double *__restrict__ e, const double r[3], const d
     } else {
         // f = -gk j with j = 1.5 J2 R^2 / r^2:  k_xy = gk (1 + j (1 - q)),  k_z = k_xy + 2 gk j   (q = 5 z^2 / r^2)
         //   = gk + j2c (gk/r^2)(1 - q),  k_z = k_xy + 2 j2c (gk/r^2): one multiply less than forming gj first
+        // (written without the factor (1 - q): a DFMA takes ONE immediate, and fma(-5, zr2, 1) made ptxas build 5.0 in a
+        // register pair with two moves per evaluation)
         const double gku = gk * ir2;
-        const double kxy = fma(KC(j2c), gku * omq, gk);
+        const double kxy = fma(KC(j2c5n), gku * zr2, fma(KC(j2c), gku, gk));
         const double kz = fma(KC(j2c2), gku, kxy);
         ax = fma(kxy, x, e[H_NIND + 0]); ay = fma(kxy, y, e[H_NIND + 1]); az = fma(kz, z, e[H_NIND + 2]);
     }
