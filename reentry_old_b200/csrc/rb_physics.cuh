@@ -270,7 +270,14 @@ template <bool FAST = false, class TB = TabGlobal>
 RB_HD double density(double altitude, double latitude_factor, double solar_time, double solar_m1, double &T_out, const TB &tb = TB()) {
     // latitude_factor = 1 + 0.01 |lat| / 90 (:76) is formed by the caller (from degrees or radians);
     // solar_m1 = solar_time - 1 (both from the time table)
+    // altitude <= 0 as an integer test of the high word (one issue cycle instead of a DSETP's two): |r| - R is either 0
+    // or at least 1e-26 in magnitude (never subnormal), so "high word <= 0" is exactly "<= 0.0"; CUDA's canonical NaN has
+    // the sign bit set and lands here too -- the lane is non-finite through its gravity term and is retired as such.
+#if defined(__CUDA_ARCH__)
+    if (FAST ? (__double2hiint(altitude) <= 0) : (altitude <= 0.0)) {
+#else
     if (altitude <= 0.0) {   // at or below the sphere of the equatorial radius (never on a live reentry's hot path)
+#endif
         T_out = RB_SEA_LEVEL_T;
 #if defined(__CUDA_ARCH__)
         // The constant is read by a VOLATILE constant-bank load: as an ordinary literal or constant-bank value the compiler
@@ -325,7 +332,12 @@ RB_HD double density(double altitude, double latitude_factor, double solar_time,
         T = fma(L, dh, lay[2]);
         const double k = lay[4];
         arg = dh * k;                                                   // isothermal: P_i e^(k dh), :84
-        if (L != 0.0) arg = k * rb_log1p_small<FAST>(lay[3] * dh);      // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
+#if defined(__CUDA_ARCH__)
+        const bool gradient = FAST ? ((__double2hiint(L) << 1) != 0) : (L != 0.0);   // (table values: 0 or |L| > 1e-4; integer test)
+#else
+        const bool gradient = L != 0.0;
+#endif
+        if (gradient) arg = k * rb_log1p_small<FAST>(lay[3] * dh);      // gradient: P_i (T/T_i)^k, T/T_i = 1 + (L/T_i) dh, :86
         c0 = lay[5] * rb_rcp(T);                                        // P / (R_GAS T), :88
     }
     T_out = T;
